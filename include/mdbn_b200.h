@@ -1,0 +1,119 @@
+/* mdbn_b200 — C ABI of the B200-native RBM / GRBM contrastive-divergence path.
+ *
+ * The reference (glgerard/MDBN) has no FFI: its hot path is Python methods that
+ * build Theano graphs.  Each entry point below replaces the Theano-compiled
+ * function behind one of those methods; the citation after "replaces:" is the
+ * reference interface (path:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 on success, non-zero on error,
+ *     message via mdbn_last_error() (thread-local).
+ *   - all tensor arguments are CALLER-OWNED DEVICE pointers, fp32, row-major;
+ *     `ld*` are row strides in elements.  W is [V,H] (src/rbm.py:100-109).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not waited on.
+ *   - the context owns only scratch memory; one context per (device, stream) user.
+ *   - samples are fp32 0.0/1.0 (src/rbm.py:210-212).
+ */
+#ifndef MDBN_B200_H
+#define MDBN_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDBN_ABI_VERSION 1
+
+typedef struct mdbn_ctx mdbn_ctx;
+
+enum { MDBN_RBM = 0, MDBN_GRBM = 1 };                       /* src/rbm.py:46 / :631 */
+enum { MDBN_RNG_NONE = 0, MDBN_RNG_BUFFER = 1, MDBN_RNG_PHILOX = 2 };
+enum { MDBN_PATH_AUTO = 0, MDBN_PATH_GENERIC = 1, MDBN_PATH_SKINNY = 2, MDBN_PATH_TENSOR = 3 };
+enum { MDBN_PHASE_FULL = 0, MDBN_PHASE_STATS = 1, MDBN_PHASE_APPLY = 2 };
+
+/* Source of randomness for one call.
+ * BUFFER: `buffer` points at this call's fp32 values, laid out as SURVEY.md App. A
+ *         ([U_h0 B*H] then per Gibbs step [U_v B*V (RBM) | N_v B*V (noisy GRBM)] [U_h B*H]);
+ *         for the single-phase calls it is just the B*H or B*V values of that phase.
+ *         Values are uniforms in (0,1) except N_v (standard normals).  Comparison is u < p.
+ * PHILOX: Philox4x32-10, key = seed, counter = (element/4, segment ordinal, offset lo, offset hi);
+ *         the caller advances `offset` by one per call. */
+typedef struct {
+  int mode;
+  const float* buffer;
+  unsigned long long seed;
+  unsigned long long offset;
+} mdbn_rng;
+
+int mdbn_abi_version(void);
+const char* mdbn_last_error(void);
+int mdbn_create(mdbn_ctx** out, int device);
+int mdbn_destroy(mdbn_ctx* ctx);
+/* number of kernels this context has launched (diagnostic; bench.py's gpu_launches) */
+unsigned long long mdbn_launch_count(const mdbn_ctx* ctx);
+
+/* pre = v W + hbias ; mean = sigmoid(pre) ; sample = (u < mean).  Any of the three
+ * outputs may be NULL (sample requires rng->mode != NONE).
+ * replaces: RBM.propup src/rbm.py:187-199, RBM.sample_h_given_v src/rbm.py:201-213,
+ *           HiddenLayer output src/mlp.py:103-107 (mean only). */
+int mdbn_propup(mdbn_ctx* ctx, const float* W, int ldw, const float* hbias,
+                const float* v, int ldv, int B, int V, int H,
+                float* pre_out, float* mean_out, float* sample_out,
+                const mdbn_rng* rng, void* stream);
+
+/* pre = h W^T + vbias.
+ * kind RBM : mean = sigmoid(pre), sample = (u < mean)              src/rbm.py:215-240
+ * kind GRBM: mean = pre (linear, unit variance); sample = mean, or mean + n with
+ *            n ~ N(0,1) when noisy != 0 (error_free=False)          src/rbm.py:647-660 */
+int mdbn_propdown(mdbn_ctx* ctx, const float* W, int ldw, const float* vbias,
+                  const float* h, int ldh, int B, int V, int H, int kind, int noisy,
+                  float* pre_out, float* mean_out, float* sample_out,
+                  const mdbn_rng* rng, void* stream);
+
+/* F[b] = -sum_j softplus(v W + hbias)_j - v.vbias            (RBM,  src/rbm.py:166-171)
+ *      = -sum_j softplus(v W + hbias)_j + 0.5 sum_i (v-vbias)^2 (GRBM, src/rbm.py:684-688) */
+int mdbn_free_energy(mdbn_ctx* ctx, const float* W, int ldw, const float* hbias, const float* vbias,
+                     const float* v, int ldv, int B, int V, int H, int kind,
+                     float* F_out, void* stream);
+
+/* One CD-k / PCD-k parameter update — the Theano function compiled from
+ * RBM.get_cost_updates (src/rbm.py:258-376) incl. compute_rbm_grad (:392-419), the
+ * lambda_1/lambda_2/momentum update (:347-365) and the monitoring cost
+ * (:421-482, :690-699). */
+typedef struct {
+  int kind;              /* MDBN_RBM | MDBN_GRBM */
+  int noisy;             /* GRBM: error_free == False                                  */
+  int B;                 /* rows in this minibatch                                      */
+  int B_nom;             /* the batch_size argument: divisor of the W statistics (:413) */
+  int V, H, k;
+  float* W;              /* [V,ldw]  updated in place */
+  int ldw;
+  float* hbias;          /* [H] */
+  float* vbias;          /* [V] */
+  float* W_speed;        /* [V,ldw]  src/rbm.py:153-162 */
+  float* hbias_speed;
+  float* vbias_speed;
+  const float* W_snap;   /* [V,ldw] frozen copy multiplied by weightcost (:414-415); NULL iff weightcost==0 */
+  const float* data;     /* dataset [N,ld_data]; v0 = data[indices] (givens, src/dbn.py:307) */
+  long long ld_data;
+  const int* indices;    /* device int32 [B], or NULL for rows 0..B-1 */
+  float* persistent;     /* PCD chain state [B,H] (ld = H) updated in place (:369), or NULL for CD */
+  int* bit_i_idx;        /* device int: pseudo-likelihood column cursor (:425,445); required iff persistent */
+  float lr, momentum, lambda_1, lambda_2, weightcost;
+  mdbn_rng rng;
+  float* cost_out;       /* device float: reconstruction cost (CD) / pseudo-likelihood (PCD) */
+  int path;              /* MDBN_PATH_* (AUTO picks by shape) */
+  int tf32;              /* allow the TF32 tensor-core path (tolerance 2e-3) */
+  int phase;             /* MDBN_PHASE_FULL, or STATS (fill stats_buf, no update) / APPLY (update from stats_buf) */
+  float* stats_buf;      /* data-parallel packing: [sum v0^T ph - nv^T nh (V*H) | sum(ph-nh) (H) | sum(v0-nv) (V) |
+                            cost numerator (1) | rows (1)], raw sums over this rank's rows */
+  int B_total;           /* APPLY: rows summed over all ranks (bias means, cost mean) */
+} mdbn_cd_args;
+
+int mdbn_cd_step(mdbn_ctx* ctx, const mdbn_cd_args* args, void* stream);
+
+/* size in floats of stats_buf for a layer */
+long long mdbn_stats_size(int V, int H);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,166 @@
+// C ABI (include/mdbn_b200.h): context management, argument validation, path dispatch.
+#include <string.h>
+#include "ctx.h"
+
+namespace mdbn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void* ws_get(mdbn_ctx* c, int slot, size_t bytes) {
+  mdbn_ctx::Buf& b = c->ws[slot];
+  if (bytes <= b.n && b.p) return b.p;
+  // Growing frees the old block: make sure nothing enqueued still uses it.
+  if (b.p) {
+    cudaDeviceSynchronize();
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.n = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    set_error("scratch slot %d: cudaMalloc(%zu) -> %s", slot, want, cudaGetErrorString(e));
+    b.p = nullptr;
+    return nullptr;
+  }
+  b.n = want;
+  return b.p;
+}
+
+}  // namespace mdbn
+
+using namespace mdbn;
+
+extern "C" {
+
+int mdbn_abi_version(void) { return MDBN_ABI_VERSION; }
+
+const char* mdbn_last_error(void) { return g_err; }
+
+int mdbn_create(mdbn_ctx** out, int device) {
+  MDBN_CHECK(out != nullptr, "mdbn_create: out is NULL");
+  int n = 0;
+  MDBN_CUDA(cudaGetDeviceCount(&n));
+  MDBN_CHECK(device >= 0 && device < n, "mdbn_create: device %d not present (%d devices)", device, n);
+  MDBN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p;
+  MDBN_CUDA(cudaGetDeviceProperties(&p, device));
+  MDBN_CHECK(p.major == 10, "mdbn_b200 is built for sm_100a only; device %d is sm_%d%d", device, p.major, p.minor);
+  mdbn_ctx* c = new mdbn_ctx();
+  c->device = device;
+  c->num_sms = p.multiProcessorCount;
+  c->l2_bytes = p.l2CacheSize;
+  MDBN_CUDA(cudaMalloc(&c->barrier, 256));
+  MDBN_CUDA(cudaMemset(c->barrier, 0, 256));
+  *out = c;
+  return 0;
+}
+
+int mdbn_destroy(mdbn_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& b : c->ws)
+    if (b.p) cudaFree(b.p);
+  if (c->barrier) cudaFree(c->barrier);
+  delete c;
+  return 0;
+}
+
+unsigned long long mdbn_launch_count(const mdbn_ctx* c) { return c ? c->launches : 0; }
+
+long long mdbn_stats_size(int V, int H) { return (long long)V * H + H + V + 2; }
+
+static int check_common(const mdbn_ctx* c, const void* W, int ldw, int B, int V, int H) {
+  MDBN_CHECK(c != nullptr, "ctx is NULL");
+  MDBN_CHECK(W != nullptr, "W is NULL");
+  MDBN_CHECK(B > 0 && V > 0 && H > 0, "bad shape B=%d V=%d H=%d", B, V, H);
+  MDBN_CHECK(ldw >= H, "ldw=%d < H=%d", ldw, H);
+  return 0;
+}
+
+int mdbn_propup(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const float* v, int ldv, int B, int V,
+                int H, float* pre_out, float* mean_out, float* sample_out, const mdbn_rng* rng, void* stream) {
+  MDBN_TRY(check_common(c, W, ldw, B, V, H));
+  MDBN_CHECK(hbias && v && ldv >= V, "propup: bad hbias/v/ldv");
+  MDBN_CHECK(!sample_out || (rng && rng->mode != MDBN_RNG_NONE), "propup: sample_out needs an rng");
+  MDBN_CHECK(!(rng && rng->mode == MDBN_RNG_BUFFER && sample_out) || rng->buffer, "propup: rng buffer is NULL");
+  MDBN_CUDA(cudaSetDevice(c->device));
+  mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
+  return generic_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
+                        make_seg(rng ? *rng : none, 0, 0), (cudaStream_t)stream);
+}
+
+int mdbn_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vbias, const float* h, int ldh, int B, int V,
+                  int H, int kind, int noisy, float* pre_out, float* mean_out, float* sample_out,
+                  const mdbn_rng* rng, void* stream) {
+  MDBN_TRY(check_common(c, W, ldw, B, V, H));
+  MDBN_CHECK(vbias && h && ldh >= H, "propdown: bad vbias/h/ldh");
+  MDBN_CHECK(kind == MDBN_RBM || kind == MDBN_GRBM, "propdown: bad kind %d", kind);
+  bool needs_rng = sample_out && (kind == MDBN_RBM || noisy);
+  MDBN_CHECK(!needs_rng || (rng && rng->mode != MDBN_RNG_NONE), "propdown: sample_out needs an rng");
+  MDBN_CHECK(!(needs_rng && rng->mode == MDBN_RNG_BUFFER) || rng->buffer, "propdown: rng buffer is NULL");
+  MDBN_CUDA(cudaSetDevice(c->device));
+  mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
+  return generic_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
+                          make_seg(rng ? *rng : none, 0, 1), (cudaStream_t)stream);
+}
+
+int mdbn_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const float* vbias, const float* v,
+                     int ldv, int B, int V, int H, int kind, float* F_out, void* stream) {
+  MDBN_TRY(check_common(c, W, ldw, B, V, H));
+  MDBN_CHECK(hbias && vbias && v && F_out && ldv >= V, "free_energy: bad arguments");
+  MDBN_CUDA(cudaSetDevice(c->device));
+  return generic_free_energy(c, W, ldw, hbias, vbias, v, ldv, B, V, H, kind, F_out, (cudaStream_t)stream);
+}
+
+int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
+  MDBN_CHECK(a != nullptr, "cd_step: args is NULL");
+  MDBN_TRY(check_common(c, a->W, a->ldw, a->B, a->V, a->H));
+  MDBN_CHECK(a->kind == MDBN_RBM || a->kind == MDBN_GRBM, "cd_step: bad kind %d", a->kind);
+  MDBN_CHECK(a->hbias && a->vbias && a->W_speed && a->hbias_speed && a->vbias_speed, "cd_step: NULL parameter/state");
+  MDBN_CHECK(a->B_nom > 0, "cd_step: batch_size (B_nom) must be given (src/rbm.py:413)");
+  MDBN_CHECK(a->phase >= MDBN_PHASE_FULL && a->phase <= MDBN_PHASE_APPLY, "cd_step: bad phase");
+  MDBN_CHECK(a->weightcost == 0.f || a->W_snap, "cd_step: weightcost != 0 needs W_snap");
+  if (a->phase != MDBN_PHASE_APPLY) {
+    MDBN_CHECK(a->k >= 1, "cd_step: k must be >= 1");
+    MDBN_CHECK(a->data && a->ld_data >= a->V, "cd_step: bad data/ld_data");
+    MDBN_CHECK(a->rng.mode == MDBN_RNG_BUFFER || a->rng.mode == MDBN_RNG_PHILOX, "cd_step: rng mode required");
+    MDBN_CHECK(a->rng.mode != MDBN_RNG_BUFFER || a->rng.buffer, "cd_step: rng buffer is NULL");
+    MDBN_CHECK(!a->persistent || a->bit_i_idx, "cd_step: PCD needs bit_i_idx");
+  }
+  if (a->phase != MDBN_PHASE_FULL) MDBN_CHECK(a->stats_buf, "cd_step: STATS/APPLY need stats_buf");
+  if (a->phase == MDBN_PHASE_APPLY) MDBN_CHECK(a->B_total > 0, "cd_step: APPLY needs B_total");
+  MDBN_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int path = a->path;
+  if (path == MDBN_PATH_AUTO) {
+    if (a->phase == MDBN_PHASE_FULL && skinny_supported(c, *a)) path = MDBN_PATH_SKINNY;
+    else if (a->tf32 && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;
+    else path = MDBN_PATH_GENERIC;
+  }
+  switch (path) {
+    case MDBN_PATH_GENERIC:
+      return generic_cd_step(c, *a, st);
+    case MDBN_PATH_SKINNY:
+      MDBN_CHECK(skinny_supported(c, *a), "cd_step: skinny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B,
+                 a->V, a->H, a->ldw, a->phase);
+      return skinny_cd_step(c, *a, st);
+    case MDBN_PATH_TENSOR:
+      MDBN_CHECK(tensor_supported(c, *a), "cd_step: tensor path does not take B=%d V=%d H=%d ldw=%d", a->B, a->V, a->H,
+                 a->ldw);
+      return tensor_cd_step(c, *a, st);
+    default:
+      set_error("cd_step: bad path %d", path);
+      return 2;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Host-side context: scratch memory + launch accounting.  One per (device, user).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+#include "common.cuh"
+
+struct mdbn_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int l2_bytes = 0;
+  unsigned long long launches = 0;
+  // named scratch arenas (grown on demand, never shrunk)
+  struct Buf { void* p = nullptr; size_t n = 0; };
+  Buf ws[16];
+  unsigned int* barrier = nullptr;   // grid barrier word for the persistent kernel
+};
+
+namespace mdbn {
+
+void set_error(const char* fmt, ...);
+
+#define MDBN_CUDA(x)                                                                   \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      mdbn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define MDBN_CHECK(cond, ...)          \
+  do {                                 \
+    if (!(cond)) {                     \
+      mdbn::set_error(__VA_ARGS__);    \
+      return 2;                        \
+    }                                  \
+  } while (0)
+
+#define MDBN_TRY(x)        \
+  do {                     \
+    int r_ = (x);          \
+    if (r_) return r_;     \
+  } while (0)
+
+enum WsSlot {
+  WS_PART = 0,   // split-K partials
+  WS_XV,         // [2B,V]  v0 ; nv_mean
+  WS_YH,         // [2B,H]  ph_mean ; nh_mean
+  WS_HS,         // [B,H]   hidden sample (chain state)
+  WS_VS,         // [B,V]   visible input of the next propup
+  WS_PREV,       // [B,V]   last pre-sigmoid visible
+  WS_G,          // [V*H + H + V + 2] packed statistics
+  WS_RED,        // small reduction partials
+  WS_XI,         // [B,V]   rounded input (pseudo-likelihood)
+  WS_PREX,       // [B,H]   pre-activation of rounded input
+  WS_SKINNY,     // persistent-kernel scratch
+  WS_TENSOR,     // tcgen05 path scratch
+  WS_MISC,
+};
+
+// grow-only scratch; returns nullptr (and sets error) on failure
+void* ws_get(mdbn_ctx* c, int slot, size_t bytes);
+
+// ---- generic (any shape, fp32-exact) path: generic.cu -----------------------
+int generic_propup(mdbn_ctx*, const float* W, int ldw, const float* hb, const float* v, int ldv, int B, int V, int H,
+                   float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
+int generic_propdown(mdbn_ctx*, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
+                     int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
+int generic_free_energy(mdbn_ctx*, const float* W, int ldw, const float* hb, const float* vb, const float* v, int ldv,
+                        int B, int V, int H, int kind, float* F, cudaStream_t st);
+int generic_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
+
+// ---- skinny persistent path (B <= 32): skinny.cu ----------------------------
+bool skinny_supported(const mdbn_ctx*, const mdbn_cd_args& a);
+int skinny_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
+
+// ---- tcgen05 / TMA path (large batch, TF32): tensor.cu ----------------------
+bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a);
+int tensor_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
+
+// layout of the App. A random buffer
+struct ULayout {
+  long long off_h0;
+  long long step_stride;   // floats per Gibbs step
+  long long off_v;         // within a step (valid if has_v)
+  long long off_h;         // within a step
+  bool has_v;
+};
+inline ULayout u_layout(int kind, int noisy, int B, int V, int H) {
+  ULayout u;
+  u.off_h0 = 0;
+  u.has_v = (kind == MDBN_RBM) || noisy;
+  u.off_v = 0;
+  u.off_h = u.has_v ? (long long)B * V : 0;
+  u.step_stride = u.off_h + (long long)B * H;
+  return u;
+}
+// segment ordinals (Philox counter word 1): 0 = positive phase, then 1+2s (visible), 2+2s (hidden)
+inline uint32_t ord_v(int s) { return 1u + 2u * (uint32_t)s; }
+inline uint32_t ord_h(int s) { return 2u + 2u * (uint32_t)s; }
+
+}  // namespace mdbn

@@ -1,0 +1,363 @@
+"""RBM / GRBM with the reference's class surface (src/rbm.py:46-728), backed by the
+sm_100a kernels behind include/mdbn_b200.h.  Eager: where the reference returns
+symbolic Theano expressions, these methods take arrays and return device tensors.
+
+Arrays in:  numpy arrays, torch tensors or `Shared`; out: fp32 CUDA tensors
+(`.cpu().numpy()` for host values).  Parameters live in `Shared` objects
+(get_value / set_value like theano.shared) and are updated IN PLACE by training.
+"""
+from __future__ import print_function, division
+
+import ctypes
+import timeit
+
+import numpy
+import torch
+
+from . import _lib
+from .rng import RandomStreams, BufferStreams, ExplicitBuffer
+from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx
+
+_PAD = 4   # W rows padded to 16 bytes so the streaming kernels can bulk-copy row slabs
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CDUpdates(dict):
+    """What get_cost_updates returns in place of Theano's `updates` dictionary: the
+    hyper-parameters of one CD-k / PCD-k step plus the state it will overwrite
+    (keys = the Shared objects, like the reference's shared-variable keys)."""
+
+    def __init__(self, rbm, **hyper):
+        super().__init__()
+        self.rbm = rbm
+        self.hyper = hyper
+        for s in rbm.params + rbm.params_speed:
+            self[s] = "in-place"
+        if hyper.get("persistent") is not None:
+            self[hyper["persistent"]] = "in-place"
+
+
+class Cost:
+    """Handle for the monitoring cost of a step (src/rbm.py:367-374)."""
+
+    def __init__(self, updates):
+        self.updates = updates
+        self.kind = "pseudo_likelihood" if updates.hyper.get("persistent") is not None else "reconstruction"
+
+
+class TrainFn:
+    """The compiled `train_rbm(indexes, momentum)` of src/rbm.py:533-544 /
+    `fn(indexes=, momentum=, lr=)` of src/dbn.py:302-312: one mdbn_cd_step per call."""
+
+    def __init__(self, rbm, updates, dataset, layer_id=0, input_fn=None, path="auto", tf32=False):
+        self.rbm, self.updates, self.layer_id = rbm, updates, layer_id
+        self.device = rbm.device
+        self.path, self.tf32 = path, tf32
+        self._dataset_arg, self._input_fn = dataset, input_fn
+        self._data, self._data_key = None, None
+        self.cost_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._cost_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._keep = None
+        self.n_calls = 0
+        self.sync = True            # return a Python float (like the reference); False -> device scalar
+
+    def data(self):
+        """Device-resident input matrix of this layer.  For a stacked layer it is the
+        deterministic up-pass of the frozen layers below (src/dbn.py:146), cached and
+        recomputed only when their parameters change."""
+        key = self._input_fn.version() if self._input_fn is not None else 0
+        if self._data is None or key != self._data_key:
+            x = as_device_matrix(self._dataset_arg, self.device)
+            self._data = self._input_fn(x) if self._input_fn is not None else x
+            self._data_key = key
+        return self._data
+
+    def __call__(self, indexes=None, momentum=0.0, lr=None, rows=None):
+        r, h = self.rbm, self.updates.hyper
+        data = self.data()
+        if isinstance(indexes, torch.Tensor):
+            idx = indexes.to(device=self.device, dtype=torch.int32)
+        else:
+            idx = torch.as_tensor(numpy.asarray(indexes, dtype=numpy.int32)).to(self.device)
+        B = int(idx.numel())
+        persistent = h.get("persistent")
+        if persistent is not None and persistent.shape[0] != B:
+            raise ValueError("PCD chain has %d rows but the minibatch has %d (the reference fails the same way)"
+                             % (persistent.shape[0], B))
+        if h["batch_size"] is None:
+            raise TypeError("batch_size=None: the W statistics are divided by batch_size (src/rbm.py:413)")
+        rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B)
+        a = _lib.CdArgs()
+        a.kind, a.noisy = r.kind, int(not getattr(r, "error_free", True))
+        a.B, a.B_nom, a.V, a.H, a.k = B, int(h["batch_size"]), r.n_visible, r.n_hidden, int(h["k"])
+        a.W, a.ldw = r.W.storage.data_ptr(), r.W.ld
+        a.hbias, a.vbias = r.hbias.data.data_ptr(), r.vbias.data.data_ptr()
+        a.W_speed = r.W_speed.storage.data_ptr()
+        a.hbias_speed, a.vbias_speed = r.hbias_speed.data.data_ptr(), r.vbias_speed.data.data_ptr()
+        snap = h.get("W_snap")
+        a.W_snap = snap.data_ptr() if snap is not None else None
+        a.data, a.ld_data, a.indices = data.data_ptr(), data.stride(0), idx.data_ptr()
+        a.persistent = persistent.data.data_ptr() if persistent is not None else None
+        a.bit_i_idx = r.bit_i_idx.data_ptr() if persistent is not None else None
+        a.lr = float(h["lr"] if lr is None else lr)
+        a.momentum = float(momentum)
+        a.lambda_1, a.lambda_2, a.weightcost = float(h["lambda_1"]), float(h["lambda_2"]), float(h["weightcost"])
+        a.rng = rng
+        a.cost_out = self.cost_dev.data_ptr()
+        a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), _lib.PHASE_FULL
+        _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
+        self._keep = (keep, idx, data)
+        self.n_calls += 1
+        for s in (r.W, r.hbias, r.vbias):
+            s.version += 1
+        if not self.sync:
+            return self.cost_dev
+        self._cost_host.copy_(self.cost_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._cost_host[0])
+
+
+class RBM(object):
+    """Restricted Boltzmann Machine (src/rbm.py:46)."""
+    kind = _lib.RBM
+
+    def __init__(self, input=None, n_visible=784, n_hidden=500, W=None, hbias=None, vbias=None,
+                 numpy_rng=None, theano_rng=None, device=None):
+        self.n_visible = n_visible
+        self.n_hidden = n_hidden
+        self.device = torch.device(device) if device is not None else default_device()
+        self.ctx = _lib.context(self.device.index if self.device.index is not None else torch.cuda.current_device())
+
+        if numpy_rng is None:
+            numpy_rng = numpy.random.RandomState(1234)                       # src/rbm.py:89
+        if theano_rng is None:
+            theano_rng = RandomStreams(numpy_rng.randint(2 ** 30))           # :92 (consumes one draw)
+        if W is None:
+            bound = 4 * numpy.sqrt(6. / (n_hidden + n_visible))              # :100-107
+            W = numpy.asarray(numpy_rng.uniform(low=-bound, high=bound, size=(n_visible, n_hidden)),
+                              dtype=numpy.float32)
+        if not isinstance(W, Shared):
+            W = Shared(W, name='W', device=self.device, ld_pad=_PAD)
+        if hbias is None:
+            hbias = numpy.zeros(n_hidden, dtype=numpy.float32)
+        if not isinstance(hbias, Shared):
+            hbias = Shared(hbias, name='hbias', device=self.device)
+        if vbias is None:
+            vbias = numpy.zeros(n_visible, dtype=numpy.float32)
+        if not isinstance(vbias, Shared):
+            vbias = Shared(vbias, name='vbias', device=self.device)
+        assert W.shape == (n_visible, n_hidden) and hbias.shape == (n_hidden,) and vbias.shape == (n_visible,)
+
+        self.input = input            # None, or a callable giving this layer's input from the DBN input
+        self.W, self.hbias, self.vbias = W, hbias, vbias
+        self.theano_rng = theano_rng
+        self.params = [self.W, self.hbias, self.vbias]
+        self.momentum = 0.0                                                   # :151
+        self.W_speed = Shared(numpy.zeros((n_visible, n_hidden), numpy.float32), name='W_speed',
+                              device=self.device, ld_pad=_PAD)               # :153-162
+        assert self.W_speed.ld == self.W.ld, "W and W_speed must share a row stride"
+        self.hbias_speed = Shared(numpy.zeros(n_hidden, numpy.float32), name='hbias_speed', device=self.device)
+        self.vbias_speed = Shared(numpy.zeros(n_visible, numpy.float32), name='vbias_speed', device=self.device)
+        self.params_speed = [self.W_speed, self.hbias_speed, self.vbias_speed]
+        self.bit_i_idx = torch.zeros(1, dtype=torch.int32, device=self.device)   # :425
+
+    @property
+    def Wt(self):
+        return self.W.data.t()                                                # :139 (a view, never materialised)
+
+    # ---- helpers -----------------------------------------------------------
+    def _mat(self, x, n):
+        t = as_device_matrix(x, self.device)
+        if t.dim() != 2 or t.shape[1] != n:
+            raise ValueError("expected a [B,%d] matrix, got %s" % (n, tuple(t.shape)))
+        return t
+
+    def _rng_for(self, u, site):
+        if u is not None:
+            return ExplicitBuffer(u).next_rng(site, self.device)
+        if isinstance(self.theano_rng, BufferStreams):
+            raise ValueError("BufferStreams drives whole CD steps; pass u=... to the single-phase sampling calls")
+        return self.theano_rng.next_rng((id(self), site), self.device)
+
+    def _propup(self, vis, want_pre=True, want_mean=True, u=None, sample=False):
+        v = self._mat(vis, self.n_visible)
+        B, H = v.shape[0], self.n_hidden
+        mk = lambda on: torch.empty((B, H), dtype=torch.float32, device=self.device) if on else None
+        pre, mean, smp = mk(want_pre), mk(want_mean), mk(sample)
+        rng, keep = self._rng_for(u, "h") if sample else (None, None)
+        _lib.check(self.ctx.lib.mdbn_propup(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
+                                            self.hbias.data.data_ptr(), v.data_ptr(), v.stride(0), B,
+                                            self.n_visible, H, _ptr(pre), _ptr(mean), _ptr(smp),
+                                            ctypes.byref(rng) if rng is not None else None, _stream()))
+        return pre, mean, smp
+
+    def _propdown(self, hid, kind, noisy=False, u=None, sample=False):
+        h = self._mat(hid, self.n_hidden)
+        B, V = h.shape[0], self.n_visible
+        mk = lambda on: torch.empty((B, V), dtype=torch.float32, device=self.device) if on else None
+        pre, mean, smp = mk(True), mk(True), mk(sample)
+        needs = sample and (kind == _lib.RBM or noisy)
+        rng, keep = self._rng_for(u, "v") if needs else (None, None)
+        _lib.check(self.ctx.lib.mdbn_propdown(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
+                                              self.vbias.data.data_ptr(), h.data_ptr(), h.stride(0), B, V,
+                                              self.n_hidden, kind, int(noisy), _ptr(pre), _ptr(mean), _ptr(smp),
+                                              ctypes.byref(rng) if rng is not None else None, _stream()))
+        return pre, mean, smp
+
+    # ---- reference surface ---------------------------------------------------
+    def free_energy(self, v_sample):
+        """src/rbm.py:166-171 (GRBM: :684-688) -> [B]"""
+        v = self._mat(v_sample, self.n_visible)
+        F = torch.empty(v.shape[0], dtype=torch.float32, device=self.device)
+        _lib.check(self.ctx.lib.mdbn_free_energy(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
+                                                 self.hbias.data.data_ptr(), self.vbias.data.data_ptr(),
+                                                 v.data_ptr(), v.stride(0), v.shape[0], self.n_visible,
+                                                 self.n_hidden, self.kind, F.data_ptr(), _stream()))
+        return F
+
+    def free_energy_gap(self, train, test):
+        """mean F(test) - mean F(train)   src/rbm.py:173-180"""
+        return self.free_energy(test).mean() - self.free_energy(train).mean()
+
+    def free_energies(self, train, test):
+        return self.free_energy(train), self.free_energy(test)               # :182-185
+
+    def propup(self, vis):
+        pre, mean, _ = self._propup(vis)                                      # :187-199
+        return [pre, mean]
+
+    def sample_h_given_v(self, v0_sample, u=None):
+        pre, mean, smp = self._propup(v0_sample, u=u, sample=True)            # :201-213
+        return [pre, mean, smp]
+
+    def propdown(self, hid):
+        pre, mean, _ = self._propdown(hid, _lib.RBM)                          # :215-227 (sigmoid, also for GRBM)
+        return [pre, mean]
+
+    def sample_v_given_h(self, h0_sample, u=None):
+        pre, mean, smp = self._propdown(h0_sample, _lib.RBM, u=u, sample=True)   # :229-240
+        return [pre, mean, smp]
+
+    def gibbs_hvh(self, h0_sample, u_v=None, u_h=None):
+        pre_v, v_mean, v_sample = self.sample_v_given_h(h0_sample, u=u_v)     # :242-248
+        pre_h, h_mean, h_sample = self.sample_h_given_v(v_sample, u=u_h)
+        return [pre_v, v_mean, v_sample, pre_h, h_mean, h_sample]
+
+    def gibbs_vhv(self, v0_sample, u_h=None, u_v=None):
+        pre_h, h_mean, h_sample = self.sample_h_given_v(v0_sample, u=u_h)     # :250-256
+        pre_v, v_mean, v_sample = self.sample_v_given_h(h_sample, u=u_v)
+        return [pre_h, h_mean, h_sample, pre_v, v_mean, v_sample]
+
+    def get_cost_updates(self, lr=0.1, k=1, lambda_1=0.0, lambda_2=0.0, weightcost=0.0,
+                         batch_size=None, persistent=None, symbolic_grad=False):
+        """One step of CD-k / PCD-k (src/rbm.py:258-376).  Returns (cost, updates): `updates`
+        describes the in-place step; `make_train_fn(dataset, cost, updates)` compiles it.
+        W_snap (the constant `weightcost` multiplies, :414-415) is captured HERE, like the
+        reference captures `self.W.get_value()` at graph-build time."""
+        if symbolic_grad:
+            raise NotImplementedError("symbolic_grad=True is never enabled by any caller of the reference "
+                                      "(src/rbm.py:341-342) and has no kernel")
+        if persistent is not None and not isinstance(persistent, Shared):
+            persistent = Shared(persistent, name='persistent', device=self.device)
+        snap = self.W.storage.clone() if weightcost != 0 else None
+        updates = CDUpdates(self, lr=lr, k=k, lambda_1=lambda_1, lambda_2=lambda_2, weightcost=weightcost,
+                            batch_size=batch_size, persistent=persistent, W_snap=snap)
+        return Cost(updates), updates
+
+    def make_train_fn(self, train_set_x, cost, updates, layer_id=0, input_fn=None, path="auto", tf32=False):
+        assert cost.updates is updates
+        return TrainFn(self, updates, train_set_x, layer_id=layer_id, input_fn=input_fn, path=path, tf32=tf32)
+
+    def training(self, train_set_x, validation_set_x, training_epochs, batch_size=10, learning_rate=0.1, k=1,
+                 initial_momentum=0.0, final_momentum=0.0, weightcost=0.0, lambda_2=0.0, persistent=True,
+                 display_fn=None, graph_output=False):
+        """src/rbm.py:484-520.  NB: `lambda_2` is accepted and not forwarded, and the default
+        is PCD with a chain of zeros, exactly like the reference (App. C-6/7)."""
+        if persistent:
+            persistent_chain = Shared(numpy.zeros((batch_size, self.n_hidden), numpy.float32), device=self.device)
+        else:
+            persistent_chain = None
+        cost, updates = self.get_cost_updates(lr=learning_rate, k=k, weightcost=weightcost,
+                                              batch_size=batch_size, persistent=persistent_chain)
+        return self.learn_model(train_set_x=train_set_x, validation_set_x=validation_set_x,
+                                training_epochs=training_epochs, batch_size=batch_size,
+                                initial_momentum=initial_momentum, final_momentum=final_momentum,
+                                cost=cost, updates=updates, display_fn=display_fn, graph_output=graph_output)
+
+    def learn_model(self, train_set_x, validation_set_x, training_epochs, batch_size,
+                    initial_momentum, final_momentum, cost, updates, display_fn, graph_output, verbose=True):
+        """Epoch loop of src/rbm.py:522-629.  Returns [(mean cost, free-energy gap)] per epoch."""
+        train_rbm = self.make_train_fn(train_set_x, cost, updates)
+        train_rbm.sync = False
+        train = train_rbm.data()
+        val = as_device_matrix(validation_set_x, self.device)
+        n_train_data, n_val = train.shape[0], val.shape[0]
+        start_time = timeit.default_timer()
+        momentum = initial_momentum
+        history = []
+        for epoch in range(training_epochs):
+            if epoch == 6:                                                    # :584 (0-based)
+                momentum = final_momentum
+            _, minibatches = get_minibatches_idx(n_train_data, batch_size, shuffle=True)
+            # one H2D copy of the whole epoch's index list instead of one per step
+            flat = torch.as_tensor(numpy.concatenate(minibatches)).to(self.device)
+            costs = torch.empty(len(minibatches), dtype=torch.float32, device=self.device)
+            lo = 0
+            for i, mb in enumerate(minibatches):
+                c = train_rbm(flat[lo:lo + len(mb)], momentum)
+                costs[i:i + 1].copy_(c)
+                lo += len(mb)
+            feg = float(self.free_energy_gap(train[:n_val], val))             # :597, :549-558
+            mean_cost = float(costs.double().mean())
+            history.append((mean_cost, feg))
+            if verbose:
+                print('Training epoch %d, cost is ' % epoch, mean_cost)
+                print('Free energy gap is ', feg)
+            if display_fn is not None:
+                display_fn(self.W.get_value(borrow=True), self.n_hidden)
+        if verbose:
+            print('Training took %f minutes' % ((timeit.default_timer() - start_time) / 60.))
+        return history
+
+
+class GRBM(RBM):
+    """Gaussian-Bernoulli RBM (src/rbm.py:631-728): linear unit-variance visibles."""
+    kind = _lib.GRBM
+
+    def __init__(self, input=None, n_visible=784, n_hidden=500, W=None, hbias=None, vbias=None,
+                 numpy_rng=None, theano_rng=None, error_free=True, device=None):
+        super(GRBM, self).__init__(input, n_visible, n_hidden, W, hbias, vbias, numpy_rng, theano_rng, device=device)
+        self.error_free = error_free
+
+    def sample_v_given_h(self, h0_sample, u=None):
+        """[v1_mean, v1_mean, v1_sample] — slot 0 is NOT a pre-sigmoid (src/rbm.py:647-660)."""
+        pre, mean, smp = self._propdown(h0_sample, _lib.GRBM, noisy=not self.error_free, u=u, sample=True)
+        return [mean, mean, smp]
+
+    def gibbs_hvh(self, h0_sample, u_v=None, u_h=None):
+        pre_v, v_mean, v_sample = self.sample_v_given_h(h0_sample, u=u_v)     # :662-671
+        pre_h, h_mean, h_sample = self.sample_h_given_v(v_mean, u=u_h)        # h given the MEAN
+        return [pre_v, v_mean, v_sample, pre_h, h_mean, h_sample]
+
+    def gibbs_vhv(self, v0_sample, u_h=None, u_v=None):
+        pre_h, h_mean, h_sample = self.sample_h_given_v(v0_sample, u=u_h)     # :673-682
+        pre_v, v_mean, v_sample = self.sample_v_given_h(h_mean, u=u_v)        # v given the MEAN
+        return [pre_h, h_mean, h_sample, pre_v, v_mean, v_sample]
+
+    def training(self, train_set_x, validation_set_x, training_epochs, batch_size=10, learning_rate=0.01, k=1,
+                 initial_momentum=0.0, final_momentum=0.0, weightcost=0.0, lambda_1=0.0, lambda_2=0.1,
+                 persistent=False, display_fn=None, graph_output=False):
+        """src/rbm.py:701-728; `persistent` is accepted and ignored like the reference (always CD)."""
+        cost, updates = self.get_cost_updates(lr=learning_rate, k=k, lambda_1=lambda_1, lambda_2=lambda_2,
+                                              weightcost=weightcost, batch_size=batch_size)
+        return self.learn_model(train_set_x=train_set_x, validation_set_x=validation_set_x,
+                                training_epochs=training_epochs, batch_size=batch_size,
+                                initial_momentum=initial_momentum, final_momentum=final_momentum,
+                                cost=cost, updates=updates, display_fn=display_fn, graph_output=graph_output)

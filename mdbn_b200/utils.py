@@ -1,0 +1,95 @@
+"""Host-side helpers on the path: minibatch index lists (src/utils.py:54-75) and the
+device-resident stand-in for theano.shared (src/rbm.py:109, src/dbn.py:172-173)."""
+import numpy
+import torch
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mdbn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Shared:
+    """A named device tensor with the get_value/set_value surface of a Theano shared
+    variable.  `data` is the live fp32 CUDA tensor the kernels update in place;
+    `version` counts in-place updates (used to invalidate cached activations)."""
+
+    def __init__(self, value, name=None, device=None, ld_pad=1):
+        device = device or default_device()
+        if isinstance(value, Shared):
+            value = value.data
+        if isinstance(value, torch.Tensor):
+            t = value.detach().to(device=device, dtype=torch.float32)
+        else:
+            t = torch.as_tensor(numpy.asarray(value, dtype=numpy.float32)).to(device)
+        if t.dim() == 2 and ld_pad > 1:
+            # rows padded to a multiple of ld_pad floats so every row starts 16-byte aligned
+            ld = (t.shape[1] + ld_pad - 1) // ld_pad * ld_pad
+            store = torch.zeros((t.shape[0], ld), dtype=torch.float32, device=device)
+            store[:, :t.shape[1]] = t
+            self.storage = store
+            self.data = store[:, :t.shape[1]]
+        else:
+            self.storage = t.contiguous().clone()      # own the memory (borrow semantics are not kept)
+            self.data = self.storage
+        self.name = name
+        self.version = 0
+
+    @property
+    def ld(self):
+        return self.storage.shape[1] if self.storage.dim() == 2 else 1
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def get_value(self, borrow=False):
+        return self.data.detach().cpu().numpy()
+
+    def set_value(self, value, borrow=False):
+        self.data.copy_(torch.as_tensor(numpy.asarray(value, dtype=numpy.float32)).to(self.data.device))
+        self.version += 1
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+    def __bool__(self):          # `if persistent:` (src/rbm.py:367) must be true for a chain of zeros
+        return True
+
+    def __repr__(self):
+        return "Shared(%s, shape=%s)" % (self.name, self.shape)
+
+
+def shared(value, name=None, borrow=False, device=None):
+    return Shared(value, name=name, device=device)
+
+
+def as_device_matrix(x, device):
+    """Dataset argument -> contiguous fp32 CUDA matrix (Shared, tensor, ndarray or anything with get_value)."""
+    if isinstance(x, Shared):
+        t = x.data
+    elif isinstance(x, torch.Tensor):
+        t = x
+    elif hasattr(x, "get_value"):
+        t = torch.as_tensor(numpy.asarray(x.get_value(borrow=True), dtype=numpy.float32))
+    else:
+        t = torch.as_tensor(numpy.asarray(x, dtype=numpy.float32))
+    t = t.to(device=device, dtype=torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def get_minibatches_idx(n, batch_size, shuffle=False):
+    """Index lists of one epoch.  Uses the GLOBAL numpy RNG for the shuffle, like the
+    reference (src/utils.py:61-62); the last minibatch is ragged when n % batch_size != 0."""
+    idx_list = numpy.arange(n, dtype="int32")
+    if shuffle:
+        numpy.random.shuffle(idx_list)
+    minibatches = []
+    start = 0
+    for _ in range(n // batch_size):
+        minibatches.append(idx_list[start:start + batch_size])
+        start += batch_size
+    if start != n:
+        minibatches.append(idx_list[start:])
+    return range(len(minibatches)), minibatches

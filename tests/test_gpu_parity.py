@@ -1,0 +1,322 @@
+"""GPU parity: the CUDA path (through the Python host -> C ABI) against the golden vectors
+of the reference-under-shim and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): mean-field activations and updates within 1e-5 relative
+in fp32; Bernoulli samples exact except where |u - p| < tolerance; costs within 1%."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import rbm_oracle as O          # noqa: E402
+from oracle import shared_u                 # noqa: E402
+
+RTOL = 1e-5
+
+
+def M():
+    import mdbn_b200
+    return mdbn_b200
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def close(actual, desired, rtol=RTOL, scale=None, what=""):
+    """|a - d| <= rtol * max(|d|, scale): relative to the tensor's magnitude, as dot products
+    are accurate relative to sum|terms|, not to a possibly cancelling result."""
+    a = actual.detach().cpu().numpy() if hasattr(actual, "detach") else np.asarray(actual)
+    d = np.asarray(desired, dtype=np.float64)
+    s = np.abs(d).max() if scale is None else scale
+    err = np.abs(a - d)
+    bound = rtol * np.maximum(np.abs(d), s) + 1e-7
+    assert (err <= bound).all(), "%s: max err %.3e (bound %.3e) at %s" % (
+        what, err.max(), bound.flat[err.argmax()], np.unravel_index(err.argmax(), err.shape))
+
+
+def samples_match(sample, mean_ref, u, what=""):
+    s = sample.detach().cpu().numpy()
+    ref = (u < mean_ref).astype(np.float64)
+    bad = s != ref
+    if bad.any():
+        assert (np.abs(u - mean_ref)[bad] < 1e-5).all(), "%s: sample flips away from |u-p|<tol" % what
+    assert set(np.unique(s)) <= {0.0, 1.0}
+
+
+def build_layer(g, W="W", rng=None):
+    m = M()
+    cls = m.GRBM if int(g["kind"]) == O.GRBM else m.RBM
+    kw = dict(error_free=bool(g["error_free"])) if cls is m.GRBM else {}
+    V, H = g[W].shape
+    return cls(n_visible=V, n_hidden=H, W=g[W].astype(np.float32), theano_rng=rng, **kw)
+
+
+@pytest.mark.parametrize("name", ["phases_rbm", "phases_grbm", "phases_grbm_noisy"])
+def test_phases_vs_golden(name):
+    g = load(name)
+    r = build_layer(g)
+    r.hbias.set_value(g["hbias"])
+    r.vbias.set_value(g["vbias"])
+    v, hid, uh, uv, nv = g["v"], g["hid"], g["uh"], g["uv"], g["nv"]
+    grbm = int(g["kind"]) == O.GRBM
+    vdraw = nv if grbm else uv
+    pre, mean = r.propup(v)
+    close(pre, g["propup"][0], what="propup pre")
+    close(mean, g["propup"][1], what="propup mean")
+    pre, mean = r.propdown(hid)
+    close(pre, g["propdown"][0], what="propdown pre")
+    close(mean, g["propdown"][1], what="propdown mean")
+    pre, mean, smp = r.sample_h_given_v(v, u=uh)
+    close(mean, g["sample_h_given_v"][1])
+    samples_match(smp, g["sample_h_given_v"][1], uh, "sample_h_given_v")
+    out = r.sample_v_given_h(hid, u=vdraw)
+    close(out[0], g["sample_v_given_h"][0])
+    close(out[1], g["sample_v_given_h"][1])
+    if grbm:
+        close(out[2], g["sample_v_given_h"][2], what="GRBM v sample")
+    else:
+        samples_match(out[2], g["sample_v_given_h"][1], uv, "sample_v_given_h")
+    out = r.gibbs_hvh(hid, u_v=vdraw, u_h=uh)
+    for j in range(2):
+        close(out[j], g["gibbs_hvh_v"][j], what="gibbs_hvh v%d" % j)
+        close(out[3 + j], g["gibbs_hvh_h"][j], what="gibbs_hvh h%d" % j)
+    samples_match(out[5], g["gibbs_hvh_h"][1], uh, "gibbs_hvh h sample")
+    out = r.gibbs_vhv(v, u_h=uh, u_v=vdraw)
+    for j in range(2):
+        close(out[j], g["gibbs_vhv_h"][j], what="gibbs_vhv h%d" % j)
+        close(out[3 + j], g["gibbs_vhv_v"][j], what="gibbs_vhv v%d" % j)
+    close(r.free_energy(v), g["free_energy"], what="free_energy")
+    close(r.free_energy_gap(v, g["v2"]), g["free_energy_gap"], scale=np.abs(g["free_energies_a"]).max())
+    fa, fb = r.free_energies(v, g["v2"])
+    close(fa, g["free_energies_a"])
+    close(fb, g["free_energies_b"])
+
+
+CD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "cd_*.npz")))
+
+
+def run_cd_golden(g, path):
+    m = M()
+    V, H, k, B_nom = int(g["V"]), int(g["H"]), int(g["k"]), int(g["B_nom"])
+    kind, ef = int(g["kind"]), bool(g["error_free"])
+    prov = lambda layer, call, b: shared_u.step_buffer(int(g["seed_u"]), int(g["layer_id"]), call, kind, ef, b, V, H, k)
+    r = build_layer(g, W="W0", rng=m.BufferStreams(prov))
+    P = m.shared(np.zeros((B_nom, H), np.float32)) if bool(g["pcd"]) else None
+    cost, upd = r.get_cost_updates(lr=float(g["lr"]), k=k, lambda_1=float(g["lambda_1"]),
+                                   lambda_2=float(g["lambda_2"]), weightcost=float(g["weightcost"]),
+                                   batch_size=B_nom, persistent=P)
+    fn = r.make_train_fn(g["data"].astype(np.float32), cost, upd, path=path)
+    costs = []
+    for t, (lo, hi) in enumerate(g["rows"]):
+        costs.append(fn(np.arange(lo, hi, dtype=np.int32), float(g["momentum"][t])))
+    return r, P, np.array(costs)
+
+
+@pytest.mark.parametrize("path", ["generic", "skinny", "auto"])
+@pytest.mark.parametrize("name", CD_CASES)
+def test_cd_sequences_vs_golden(name, path):
+    g = load(name)
+    r, P, costs = run_cd_golden(g, path)
+    np.testing.assert_allclose(costs, g["costs"], rtol=2e-4, atol=1e-5)
+    wscale = np.abs(g["W"]).max()
+    close(r.W.get_value(), g["W"], rtol=2e-5, scale=wscale, what="W")
+    close(r.hbias.get_value(), g["hbias"], rtol=2e-5, scale=max(np.abs(g["hbias"]).max(), 1e-3), what="hbias")
+    close(r.vbias.get_value(), g["vbias"], rtol=2e-5, scale=max(np.abs(g["vbias"]).max(), 1e-3), what="vbias")
+    close(r.W_speed.get_value(), g["W_speed"], rtol=2e-5, scale=np.abs(g["W_speed"]).max(), what="W_speed")
+    close(r.hbias_speed.get_value(), g["hbias_speed"], rtol=2e-5, scale=np.abs(g["hbias_speed"]).max())
+    close(r.vbias_speed.get_value(), g["vbias_speed"], rtol=2e-5, scale=np.abs(g["vbias_speed"]).max())
+    if P is not None:
+        np.testing.assert_array_equal(P.get_value(), g["persistent"])
+
+
+# ---------------------------------------------------------------------------
+# config shapes: CUDA vs the float64 oracle on the same seeded inputs
+# ---------------------------------------------------------------------------
+def synth(kind, n, V, seed):
+    rs = np.random.RandomState(seed)
+    if kind == O.GRBM:
+        x = rs.randn(n, V)
+        return ((x - x.mean(0)) / x.std(0)).astype(np.float32)
+    return (rs.rand(n, V) < 0.13).astype(np.float32)
+
+
+CONFIG_SHAPES = [
+    # name, kind, V, H, B, k, pcd, lr, mom, l1, l2, wc
+    ("cfg1_mnist_cd1", O.RBM, 784, 500, 20, 1, False, 0.1, 0.6, 0.0, 0.0, 0.0002),
+    ("cfg1_mnist_pcd1", O.RBM, 784, 500, 20, 1, True, 0.1, 0.6, 0.0, 0.0, 0.0002),
+    ("cfg2_ge_pcd1_b10", O.GRBM, 19937, 400, 10, 1, True, 0.005, 0.0, 0.01, 0.1, 0.0),
+    ("cfg2_ge_cd1_b20", O.GRBM, 19937, 400, 20, 1, False, 0.005, 0.0, 0.01, 0.1, 0.0),
+    ("cfg4_me_cd10", O.GRBM, 559, 40, 20, 10, False, 0.005, 0.0, 0.01, 0.01, 0.0),
+    ("cfg4_sm_cd1", O.GRBM, 1686, 200, 20, 1, False, 0.005, 0.0, 0.01, 0.01, 0.0),
+    ("cfg4_top_cd1", O.RBM, 100, 24, 20, 1, False, 0.1, 0.6, 0.0, 0.0, 0.0002),
+    ("cfg4_top2_cd1", O.RBM, 24, 3, 20, 1, False, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("cfg3_dbn_l1", O.RBM, 1000, 1000, 20, 1, False, 0.01, 0.9, 0.0, 0.0, 0.0002),
+    ("cfg5_b128_k2", O.RBM, 784, 500, 128, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("odd_shapes", O.RBM, 77, 13, 7, 3, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
+    ("odd_shapes_g", O.GRBM, 131, 30, 3, 2, True, 0.01, 0.3, 0.02, 0.05, 0.001),
+]
+
+
+@pytest.mark.parametrize("path", ["generic", "auto"])
+@pytest.mark.parametrize("cfg", CONFIG_SHAPES, ids=[c[0] for c in CONFIG_SHAPES])
+def test_config_shapes_vs_oracle(cfg, path):
+    name, kind, V, H, B, k, pcd, lr, mom, l1, l2, wc = cfg
+    m = M()
+    n_steps = 3
+    data = synth(kind, B * n_steps, V, seed=len(name))
+    L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(123), dtype=np.float64)
+    # parity is on fp32-representable inputs: both sides start from the same fp32 W
+    L.W[...] = L.W.astype(np.float32)
+    W0 = L.W.copy()
+    prov = lambda layer, call, b: shared_u.step_buffer(99, layer, call, kind, True, b, V, H, k)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    r = cls(n_visible=V, n_hidden=H, W=W0.astype(np.float32), theano_rng=m.BufferStreams(prov))
+    P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+    Po = np.zeros((B, H)) if pcd else None
+    cost, upd = r.get_cost_updates(lr=lr, k=k, lambda_1=l1, lambda_2=l2, weightcost=wc, batch_size=B, persistent=P)
+    fn = r.make_train_fn(data, cost, upd, path=path)
+    for t in range(n_steps):
+        idx = np.arange(t * B, (t + 1) * B, dtype=np.int32)
+        c = fn(idx, mom)
+        co = O.cd_step(L, data[idx].astype(np.float64), prov(0, t, B), lr=lr, k=k, lambda_1=l1, lambda_2=l2,
+                       weightcost=wc, batch_size=B, momentum=mom, persistent=Po, W_snap=W0)
+        assert abs(c - co) <= 1e-2 * abs(co), "step %d cost %r vs oracle %r" % (t, c, co)   # the 1% bar
+        assert abs(c - co) <= 2e-4 * abs(co) + 1e-5, "step %d cost %r vs oracle %r" % (t, c, co)
+        # the speeds ARE the (regularised) gradient: the tightest check of the statistics
+        close(r.W_speed.get_value(), L.W_speed, rtol=3e-5, scale=np.abs(L.W_speed).max(), what="W_speed step %d" % t)
+        if Po is not None:
+            flips = (P.get_value() != Po).sum()
+            assert flips == 0, "step %d: %d persistent-chain flips" % (t, flips)
+    close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W")
+    close(r.hbias.get_value(), L.hbias, rtol=3e-5, scale=max(np.abs(L.hbias).max(), 1e-4), what="hbias")
+    close(r.vbias.get_value(), L.vbias, rtol=3e-5, scale=max(np.abs(L.vbias).max(), 1e-4), what="vbias")
+
+
+# ---------------------------------------------------------------------------
+# DBN / MDBN loops vs the reference-under-shim
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dbn_gauss", "dbn_bern"])
+def test_dbn_training_vs_golden(name):
+    g = load(name)
+    m = M()
+    sizes = [int(s) for s in g["sizes"]]
+    k, B = int(g["k"]), int(g["B"])
+    kinds = [O.GRBM if (i == 0 and bool(g["gauss"])) else O.RBM for i in range(len(sizes))]
+    dims = [int(g["n_ins"])] + sizes
+
+    def prov(layer, call, b):
+        return shared_u.step_buffer(int(g["seed_u"]), layer, call, kinds[layer], True, b, dims[layer], dims[layer + 1], k)
+    d = m.DBN(numpy_rng=np.random.RandomState(int(g["seed"])), theano_rng=m.BufferStreams(prov), n_ins=dims[0],
+              gauss=bool(g["gauss"]), hidden_layers_sizes=sizes[:-1], n_outs=sizes[-1], verbose=False)
+    for i, L in enumerate(d.rbm_layers):
+        np.testing.assert_allclose(L.W.get_value(), g["W0_%d" % i].astype(np.float32), rtol=0, atol=0)
+    np.random.seed(int(g["shuffle_seed"]))
+    hist = d.training(g["train"].astype(np.float32), B, k, [int(e) for e in g["epochs"]],
+                      [float(x) for x in g["lrs"]], lambda_1=float(g["lambda_1"]), lambda_2=float(g["lambda_2"]),
+                      validation_set_x=g["val"].astype(np.float32) if "val" in g else None)
+    assert [h["calls"] for h in hist] == list(g["n_calls"]), "early stopping fired at a different iteration"
+    printed = [c for h in hist for (_, c, _) in h["validations"]]
+    np.testing.assert_allclose(printed, g["printed_costs"], rtol=1e-3)
+    fegs = [f for h in hist for (_, _, f) in h["validations"] if f is not None]
+    np.testing.assert_allclose(fegs, g["printed_fegs"], rtol=1e-2, atol=1e-3)
+    for i, L in enumerate(d.rbm_layers):
+        close(L.W.get_value(), g["W_%d" % i], rtol=1e-4, scale=np.abs(g["W_%d" % i]).max(), what="W_%d" % i)
+        close(L.hbias.get_value(), g["b_%d" % i], rtol=1e-4, scale=max(np.abs(g["b_%d" % i]).max(), 1e-3))
+        close(L.vbias.get_value(), g["vb_%d" % i], rtol=1e-4, scale=max(np.abs(g["vb_%d" % i]).max(), 1e-3))
+    close(d.get_output(g["train"].astype(np.float32)), g["out_train"], rtol=1e-4, scale=1.0)
+
+
+def test_mdbn_vs_golden():
+    g = load("mdbn_small")
+    m = M()
+    specs = {"ME": (15, [6], [40], [0.005], 2, 0.01, 0.01), "GE": (31, [10, 6], [60, 30], [0.005, 0.1], 1, 0.01, 0.1)}
+    rng = np.random.RandomState(123)
+    tops = []
+    for li, (mn, (V, sizes, ep, lr, k, l1, l2)) in enumerate(specs.items()):
+        dims = [V] + sizes
+
+        def prov(layer, call, b, li=li, dims=dims, k=k):
+            kind = O.GRBM if layer == 0 else O.RBM
+            return shared_u.step_buffer(int(g["seed_u"]), 10 * (li + 1) + layer, call, kind, True, b,
+                                        dims[layer], dims[layer + 1], k)
+        # train_bottom_layer builds its DBN internally; the rng streams object is injected through a
+        # DBN subclass-free hook: MDBN.train_bottom_layer accepts the numpy rng only, so patch RandomStreams
+        import mdbn_b200.dbn as dbn_mod
+        orig = dbn_mod.RandomStreams
+        dbn_mod.RandomStreams = lambda seed, prov=prov: m.BufferStreams(prov)
+        try:
+            np.random.seed(1000 + li)
+            d, out_tr, _ = m.MDBN.train_bottom_layer(g[mn + "_data"].astype(np.float32), None, batch_size=5, k=k,
+                                                     layers_sizes=sizes, pretraining_epochs=ep, pretrain_lr=lr,
+                                                     lambda_1=l1, lambda_2=l2, rng=rng, verbose=False)
+        finally:
+            dbn_mod.RandomStreams = orig
+        for i, L in enumerate(d.rbm_layers):
+            close(L.W.get_value(), g["%s_W_%d" % (mn, i)], rtol=1e-4, scale=np.abs(g["%s_W_%d" % (mn, i)]).max())
+        close(out_tr, g[mn + "_out"], rtol=1e-4, scale=1.0)
+        tops.append(g[mn + "_out"])          # teacher-forced: the joint layer trains on the reference's activations
+    joint = np.concatenate(tops, axis=1).astype(np.float32)
+
+    def prov_top(layer, call, b):
+        dims = [joint.shape[1], 24, 3]
+        return shared_u.step_buffer(int(g["seed_u"]), 90 + layer, call, O.RBM, True, b, dims[layer], dims[layer + 1], 1)
+    import mdbn_b200.dbn as dbn_mod
+    orig = dbn_mod.RandomStreams
+    dbn_mod.RandomStreams = lambda seed: m.BufferStreams(prov_top)
+    try:
+        np.random.seed(2000)
+        top = m.MDBN.train_top(5, False, joint, None, rng, verbose=False)
+    finally:
+        dbn_mod.RandomStreams = orig
+    for i, L in enumerate(top.rbm_layers):
+        # 800 dependent iterations of a chaotic stochastic system in fp32 vs fp64: a single
+        # Bernoulli flip (|u-p| ~ 1e-7) decorrelates the tail, so this is a tracking check
+        ref = g["top_W_%d" % i]
+        err = np.abs(L.W.get_value() - ref).max() / np.abs(ref).max()
+        assert err < 5e-2, "top layer %d drifted: %.3e" % (i, err)
+
+
+# ---------------------------------------------------------------------------
+# production RNG (Philox4x32-10 in-kernel)
+# ---------------------------------------------------------------------------
+def test_philox_sampling_statistics_and_determinism():
+    m = M()
+    V, H, B = 64, 4096, 64
+    r1 = m.RBM(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(1), theano_rng=m.RandomStreams(42))
+    r2 = m.RBM(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(1), theano_rng=m.RandomStreams(42))
+    v = np.zeros((B, V), np.float32)          # pre = 0 -> p = 0.5 everywhere
+    _, mean, s1 = r1.sample_h_given_v(v)
+    _, _, s1b = r1.sample_h_given_v(v)
+    s1, s1b = s1.cpu().numpy(), s1b.cpu().numpy()
+    assert abs(s1.mean() - 0.5) < 5 * 0.5 / np.sqrt(s1.size)
+    assert (s1 != s1b).mean() > 0.4           # successive calls advance the stream
+    assert abs(np.corrcoef(s1[:, :-1].ravel(), s1[:, 1:].ravel())[0, 1]) < 0.01
+
+
+def test_size_independent_properties_full_size():
+    """At BASELINE config-2 size (19937x400): (i) with lr = 0 the parameters do not move but the speeds
+    take the gradient; (ii) STATS over two half-batches sums to STATS over the whole batch (linearity,
+    the data-parallel contract); (iii) a step is deterministic run to run."""
+    m = M()
+    V, H, B = 19937, 400, 20
+    data = synth(O.GRBM, B, V, seed=5)
+    prov = lambda layer, call, b: shared_u.step_buffer(5, 0, 0, O.GRBM, True, b, V, H, 1)
+    outs = []
+    for rep in range(2):
+        r = m.GRBM(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(9), theano_rng=m.BufferStreams(prov))
+        W0 = r.W.get_value()
+        cost, upd = r.get_cost_updates(lr=0.0, k=1, lambda_1=0.0, lambda_2=0.0, batch_size=B)
+        fn = r.make_train_fn(data, cost, upd)
+        c = fn(np.arange(B, dtype=np.int32), 0.0)
+        np.testing.assert_array_equal(r.W.get_value(), W0)
+        outs.append((c, r.W_speed.get_value()))
+    assert outs[0][0] == outs[1][0]
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    assert np.abs(outs[0][1]).max() > 0
