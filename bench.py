@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — RBM CD-k training samples/sec/layer on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one full CD-k / PCD-k parameter update (positive phase, k Gibbs steps, statistics,
+lambda_1/lambda_2/momentum update, monitoring cost) of one layer on one minibatch.
+
+Default workload (N=1): BASELINE.json configs[1] — Gaussian-Bernoulli RBM 19937->400 (AML
+gene-expression shape), PCD-1, batch 10, on synthetic z-scored data [170,19937].
+With N>1 every rank trains its own layer of that shape (the path shards by independent
+layers/modalities; no data-path collective) -> weak scaling.
+
+Timing hygiene: W >= 3 warm-up steps; the timed steps rotate over 4 independent parameter sets
+(4 x (W + W_speed) = 255 MB > the 126 MB L2) so every step streams its weights from HBM; CUDA
+events on the launching stream; barrier + synchronize on both sides; max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RBM CD-k training samples/sec/layer"
+WORKLOADS = {
+    # name: kind, V, H, B, k, pcd, N rows, lr, momentum, lambda_1, lambda_2, weightcost
+    "ge_grbm_pcd1_b10": dict(kind=1, V=19937, H=400, B=10, k=1, pcd=True, N=170, lr=0.005, mom=0.0, l1=0.01,
+                             l2=0.1, wc=0.0),
+    "ge_grbm_cd1_b20": dict(kind=1, V=19937, H=400, B=20, k=1, pcd=False, N=170, lr=0.005, mom=0.0, l1=0.01,
+                            l2=0.1, wc=0.0),
+    "mnist_rbm_cd1_b20": dict(kind=0, V=784, H=500, B=20, k=1, pcd=False, N=49940, lr=0.1, mom=0.9, l1=0.0,
+                              l2=0.0, wc=0.0002),
+    "mnist_rbm_pcd1_b20": dict(kind=0, V=784, H=500, B=20, k=1, pcd=True, N=49940, lr=0.1, mom=0.9, l1=0.0,
+                               l2=0.0, wc=0.0002),
+}
+DEFAULT = "ge_grbm_pcd1_b10"
+
+
+def synth(kind, n, V, seed):
+    rs = np.random.RandomState(seed)
+    if kind == 1:
+        x = rs.randn(n, V).astype(np.float32)
+        return ((x - x.mean(0)) / x.std(0)).astype(np.float32)     # per-feature z-score (src/utils.py:96)
+    return (rs.rand(n, V) < 0.13).astype(np.float32)
+
+
+def algorithmic_bytes(w):
+    """4*[(2k+5) V H + B V + (2k+1)(V+H) + 4 (V+H)] bytes per CD-k step."""
+    V, H, B, k = w["V"], w["H"], w["B"], w["k"]
+    return 4 * ((2 * k + 5) * V * H + B * V + (2 * k + 1) * (V + H) + 4 * (V + H))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        hi = [s for s in sm if s > 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_step_rate(w, seconds=15.0, max_steps=60, warmup=1):
+    """The oracle port (NumPy fp32, OpenBLAS threads) timed on this host's cores."""
+    from oracle import rbm_oracle as O, shared_u
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    kind, V, H, B, k = w["kind"], w["V"], w["H"], w["B"], w["k"]
+    data = synth(kind, max(w["N"] if w["N"] < 1000 else 1000, B), V, 1)
+    L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(123), dtype=np.float32)
+    snap = L.W.copy()
+    P = np.zeros((B, H), np.float32) if w["pcd"] else None
+    U = shared_u.step_buffer(1, 0, 0, kind, True, B, V, H, k)
+    rs = np.random.RandomState(0)
+    times = []
+    t_end = time.perf_counter() + seconds
+    n = 0
+    while n < max_steps + warmup and (time.perf_counter() < t_end or n < warmup + 3):
+        idx = rs.randint(0, data.shape[0], B)
+        t0 = time.perf_counter()
+        O.cd_step(L, data[idx], U, lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
+                  batch_size=B, momentum=w["mom"], persistent=P, W_snap=snap)
+        dt = time.perf_counter() - t0
+        if n >= warmup:
+            times.append(dt)
+        n += 1
+    med = float(np.median(times))
+    return B / med, cores, len(times), med
+
+
+def run_reference(args, w, wname):
+    """--impl reference: the reference's CPU path for this step.  Theano cannot be installed here
+    (SURVEY.md 8c), so this is the oracle PORT (NumPy restatement pinned to the reference source,
+    oracle/rbm_oracle.py) on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0
+    v, cores, n, med = cpu_step_rate(w, seconds=budget, max_steps=max(args.steps, 3), warmup=min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "layer": "%d->%d" % (w["V"], w["H"]), "batch": w["B"], "k": w["k"],
+                   "pcd": w["pcd"]},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d CD steps of the workload timed (median), NumPy/OpenBLAS fp32 oracle port; "
+                                   "Theano itself is not installable" % n},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", type=int, default=4)
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w, args.workload)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import mdbn_b200 as M
+    from mdbn_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, V, H, B, k = w["kind"], w["V"], w["H"], w["B"], w["k"]
+    data_h = synth(kind, min(w["N"], 4096), V, 1 + rank)
+    data = torch.from_numpy(data_h).to(dev)
+    cls = M.GRBM if kind == 1 else M.RBM
+    R = max(1, args.replicas)
+    fns, layers = [], []
+    for r in range(R):
+        m = cls(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(123 + r),
+                theano_rng=M.RandomStreams(1000 + 17 * r + rank))
+        P = M.shared(np.zeros((B, H), np.float32)) if w["pcd"] else None
+        cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
+                                       batch_size=B, persistent=P)
+        fn = m.make_train_fn(data, cost, upd)
+        fn.sync = False
+        fns.append(fn)
+        layers.append(m)
+    ctx = layers[0].ctx
+    n_rows = data.shape[0]
+    n_mb = n_rows // B
+    rs = np.random.RandomState(5)
+    perm = torch.from_numpy(rs.permutation(n_rows)[: n_mb * B].astype(np.int32)).to(dev)
+    mbs = [perm[i * B:(i + 1) * B] for i in range(n_mb)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, rotate):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for s in range(n_steps):
+            fns[s % R if rotate else 0](mbs[s % n_mb], w["mom"])
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    timed(args.warmup, True)                                   # warm-up (untimed)
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.15)
+    l0 = ctx.launches
+    ms = timed(args.steps, True)                               # ---- the timed region ----
+    launches = ctx.launches - l0
+    # keep the GPU busy a little longer so that the 50 ms clock sampler sees it under load
+    t_hold = time.time() + 0.6
+    while time.time() < t_hold:
+        timed(50, True)
+    clocks = sampler.stop() if sampler else None
+    ms_warm = timed(args.steps, False)                         # same step, single parameter set (L2-warm)
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end: host minibatch -> pinned -> H2D -> step -> D2H cost, every step ----
+    host_mb = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, B)])).pin_memory() for _ in range(8)]
+    stage = torch.empty((B, V), dtype=torch.float32, device=dev)
+    e2e_fns = []
+    for r in range(R):
+        m = layers[r]
+        P = M.shared(np.zeros((B, H), np.float32)) if w["pcd"] else None
+        cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
+                                       batch_size=B, persistent=P)
+        e2e_fns.append(m.make_train_fn(stage, cost, upd))       # sync=True: returns the cost as a Python float
+    rows = torch.arange(B, dtype=torch.int32, device=dev)
+    n_e2e = min(args.steps, 400)
+
+    def e2e_loop(n):
+        acc = 0.0
+        for s in range(n):
+            stage.copy_(host_mb[s % len(host_mb)], non_blocking=True)
+            acc += e2e_fns[s % R](rows, w["mom"])
+        return acc
+    e2e_loop(max(3, args.warmup // 2))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(n_e2e)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * B * n_e2e / t_e2e
+
+    if rank == 0:
+        peak, how = peaks()
+        abytes = algorithmic_bytes(w)
+        achieved = abytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "layer": "%s %d->%d" % ("GRBM" if kind else "RBM", V, H),
+                       "batch": B, "k": k, "pcd": w["pcd"], "rng": "philox4x32-10 in-kernel",
+                       "l2": "steps rotate over %d independent parameter sets (%.0f MB > L2) so weights stream from HBM"
+                             % (R, R * 2 * V * H * 4 / 1e6),
+                       "parallelism": "one independent layer per GPU (modality-parallel), no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": 4,
+                    "steps": n_e2e, "path": "RBM.make_train_fn -> mdbn_cd_step (C ABI), host minibatch from pinned memory"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "cd_skinny_kernel", "peak_source": how,
+                         "algorithmic_bytes_per_launch": abytes,
+                         "achieved_l2_warm": abytes / (ms_warm / args.steps * 1e-3) / 1e9},
+            "value_l2_warm": world * B / (ms_warm / args.steps * 1e-3),
+        }
+        if not args.no_cpu_baseline:
+            v, cores, n, med = cpu_step_rate(w)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": "%d CD steps of the same workload (median %.1f ms/step), NumPy/OpenBLAS "
+                                              "fp32 oracle port standing in for Theano" % (n, med * 1e3)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
