@@ -17,6 +17,7 @@
 //     are read once and written once; v0 and nv slabs never left shared memory.
 // HBM traffic per step: (k+1) reads of W + read W,S + write W,S (+ read W_snap) versus the
 // (2k+1)+4 of an unfused implementation.
+#include <stdlib.h>
 #include "ctx.h"
 
 namespace mdbn {
@@ -53,6 +54,7 @@ struct Params {
   float *PH, *NH, *HS, *PREX;   // [BT][ldw], zero-initialised, padded columns never written
   float* cost_part;   // [gridDim]
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
+  unsigned long long* dbg;   // optional phase timeline (MDBN_SKINNY_TIMING=1), CTA 0 only
   // smem byte offsets
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc;
 };
@@ -170,6 +172,15 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   const bool col_ok = grp_ok && q < p.CQ;
   const int wg = (p.GW >= 32) ? (warp % (p.GW >> 5)) : 0;   // warp index inside its group
   unsigned long long bar_target = 0;
+  int dbg_i = 0;
+  auto mark = [&]() {
+    if (p.dbg && cta == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[dbg_i++] = t;
+    }
+  };
+  mark();
 
   Ring ring{smem, bars, 0u};
   if (tid == 0) {
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 
   // ---- tile pipeline helpers -------------------------------------------------
   // job j of a pass loads `narr` arrays (W [, S [, Wsnap]]) of tile j into consecutive slots.
-  auto issue = [&](int j, int narr, int depth) {
+  auto issue = [&](int j, int narr, int depth) {      // thread 0 only; jobs are issued in order j = 0,1,2,...
     if (j >= ntiles) return;
     int st = j % depth;
     int r0 = j * p.TR, nr = min(p.TR, rows - r0);
@@ -193,8 +204,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     if (narr > 1) bulk_g2s(dst + SLOT, p.S + goff, bytes, bar);
     if (narr > 2) bulk_g2s(dst + 2 * SLOT, p.Wsnap + goff, bytes, bar);
   };
-  auto wait_tile = [&](int j, int depth) {
-    int st = j % depth;
+  auto wait_stage = [&](int st) {
     mbar_wait(&ring.bars[st], (ring.phase_bits >> st) & 1u);
     ring.phase_bits ^= (1u << st);
   };
@@ -217,12 +227,14 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       x = p.data[dr * p.ld_data + row0 + r];
     }
     v0s[r * BTP + b] = x;
+    if (p.pcd) nvs[r * BTP + b] = roundf(x);   // src/rbm.py:428; slab is free until the last Gibbs step
   }
   __syncthreads();
 
   // ---- propup accumulation of one staged tile: acc[b] += src[r][b] * W[r, 4q..4q+3] -------
-  auto up_tile = [&](const float4* __restrict__ tile, const float* __restrict__ src, int nr, float4 (&acc)[BT],
-                     bool rounded) {
+  // DUAL: a second input slab (round(v0), pseudo-likelihood) shares the W loads.
+  auto up_tile = [&](const float4* __restrict__ tile, const float* __restrict__ src, const float* __restrict__ src2,
+                     int nr, float4 (&acc)[BT], float4 (&acc2)[BT], bool dual) {
     if (!col_ok) return;
     for (int r = g; r < nr; r += p.G) {
       float4 w = tile[r * ldw4 + q];
@@ -235,11 +247,28 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         for (int t = 0; t < 4; ++t) {
           const int b = b4 * 4 + t;
           if (b < BT) {
-            float x = rounded ? roundf(xs[t]) : xs[t];
-            acc[b].x = fmaf(x, w.x, acc[b].x);
-            acc[b].y = fmaf(x, w.y, acc[b].y);
-            acc[b].z = fmaf(x, w.z, acc[b].z);
-            acc[b].w = fmaf(x, w.w, acc[b].w);
+            acc[b].x = fmaf(xs[t], w.x, acc[b].x);
+            acc[b].y = fmaf(xs[t], w.y, acc[b].y);
+            acc[b].z = fmaf(xs[t], w.z, acc[b].z);
+            acc[b].w = fmaf(xs[t], w.w, acc[b].w);
+          }
+        }
+      }
+      if (dual) {
+        const float4* xr = reinterpret_cast<const float4*>(src2 + r * BTP);
+#pragma unroll
+        for (int b4 = 0; b4 < BTP / 4; ++b4) {
+          float4 vv = xr[b4];
+          float xs[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int b = b4 * 4 + t;
+            if (b < BT) {
+              acc2[b].x = fmaf(xs[t], w.x, acc2[b].x);
+              acc2[b].y = fmaf(xs[t], w.y, acc2[b].y);
+              acc2[b].z = fmaf(xs[t], w.z, acc2[b].z);
+              acc2[b].w = fmaf(xs[t], w.w, acc2[b].w);
+            }
           }
         }
       }
@@ -329,6 +358,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     __syncthreads();
   };
 
+  mark();   // gather done
   // =============================== pass 0: positive phase ===============================
   {
     const int depth = p.nslots;
@@ -336,23 +366,27 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     float4 acc[BT], acc2[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = acc2[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < ntiles; ++j) {
-      wait_tile(j, depth);
-      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)(j % depth) * SLOT);
+    for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
+      wait_stage(st);
+      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)st * SLOT);
       int nr = min(p.TR, rows - j * p.TR);
-      up_tile(tile, v0s + (size_t)j * p.TR * BTP, nr, acc, false);
-      if (p.pcd) up_tile(tile, v0s + (size_t)j * p.TR * BTP, nr, acc2, true);
+      up_tile(tile, v0s + (size_t)j * p.TR * BTP, nvs + (size_t)j * p.TR * BTP, nr, acc, acc2, p.pcd != 0);
       __syncthreads();
       if (tid == 0) issue(j + depth, 1, depth);
     }
+    mark();   // pass-0 tiles done
     flush_partial(acc, 0);
     if (p.pcd) flush_partial(acc2, 1);
   }
+  mark();
   grid_sync(p.bar, bar_target);
+  mark();
   // CD: chain starts from the fresh sample; PCD: from the persistent chain (src/rbm.py:308-311)
   reduce_hidden(p.pcd ? 2 : 1, p.PH, seg(0, 0), !p.pcd, false);
+  mark();   // reduce 0 done
   grid_sync(p.bar, bar_target);
   if (p.pcd) load_hs(p.P, H, B); else load_hs(p.HS, ldw, BT);
+  mark();
 
   // pseudo-likelihood monitor (src/rbm.py:421-447) — CTA 0, uses the pre-update W, hb, vb
   if (p.pcd && cta == 0) {
@@ -403,9 +437,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int j = 0; j < ntiles; ++j) {
-      wait_tile(j, depth);
-      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)(j % depth) * SLOT);
+    for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
+      wait_stage(st);
+      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)st * SLOT);
       const int nr = min(p.TR, rows - j * p.TR);
       // ---- propdown of the tile rows: partial dot over this thread's 4 columns, then across lanes
       if (grp_ok) {
@@ -483,18 +517,21 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       }
       __syncthreads();
       // ---- propup accumulation from the same tile ----
-      up_tile(tile, vt, nr, acc, false);
+      up_tile(tile, vt, vt, nr, acc, acc, false);
       __syncthreads();
       if (tid == 0) issue(j + depth, 1, depth);
     }
+    if (last) mark();   // Gibbs tiles done
     flush_partial(acc, 0);
     if (last && !p.pcd) {
       float c = block_sum(cost_acc, misc);
       if (tid == 0) __stcg(&p.cost_part[cta], c);
     }
     grid_sync(p.bar, bar_target);
+    if (last) mark();
     reduce_hidden(1, p.NH, rs_h, !last, last && p.pcd);
     grid_sync(p.bar, bar_target);
+    if (last) mark();
     if (!last) load_hs(p.HS, ldw, BT);
   }
 
@@ -514,9 +551,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       }
     }
     const int ncol = min(4, H - 4 * q);
-    for (int j = 0; j < ntiles; ++j) {
-      wait_tile(j, depth);
-      const unsigned char* sb = ring.base + (size_t)(j % depth) * narr * SLOT;
+    for (int j = 0, stg = 0; j < ntiles; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
+      wait_stage(stg);
+      const unsigned char* sb = ring.base + (size_t)stg * narr * SLOT;
       const float4* wt = reinterpret_cast<const float4*>(sb);
       const float4* st = reinterpret_cast<const float4*>(sb + SLOT);
       const float4* sn = reinterpret_cast<const float4*>(sb + 2 * SLOT);
@@ -550,9 +587,13 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float gw = gv[c] * p.inv_bnom - p.wc * snv[c];                // src/rbm.py:411-415
-            float D = 1.0f + p.c1 / (fabsf(wv[c]) + 0.001f);              // :347-350
-            gw = gw / D;
-            float mult = p.decay / D;                                     // :353-356
+            float mult = p.decay;
+            if (p.c1 != 0.f) {
+              // D = 1 + 2 lr lambda_1 / (|W| + eps); MUFU reciprocals (<= 2 ulp) instead of IEEE division
+              float invD = __fdividef(1.0f, 1.0f + p.c1 * __fdividef(1.0f, fabsf(wv[c]) + 0.001f));   // :347-350
+              gw *= invD;
+              mult *= invD;                                               // :353-356
+            }
             so[c] = gw + (sv[c] - gw) * p.mom;                            // :361
             wo[c] = wv[c] * mult + sv[c] * p.lr;                          // :364 (OLD speed)
           }
@@ -602,6 +643,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     }
   }
 
+  mark();   // stats + update done
   // reset the barrier for the next launch: the last CTA out switches off the lights
   __syncthreads();
   if (tid == 0) {
@@ -749,16 +791,27 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.PREX = p.HS + hb_f;
   p.cost_part = p.PREX + hb_f;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);
+  static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
+  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;
+  int rc = 2;
   switch (g.BT) {
-    case 4: return sk::launch<4>(c, p, g, st);
-    case 8: return sk::launch<8>(c, p, g, st);
-    case 10: return sk::launch<10>(c, p, g, st);
-    case 12: return sk::launch<12>(c, p, g, st);
-    case 16: return sk::launch<16>(c, p, g, st);
-    case 20: return sk::launch<20>(c, p, g, st);
+    case 4: rc = sk::launch<4>(c, p, g, st); break;
+    case 8: rc = sk::launch<8>(c, p, g, st); break;
+    case 10: rc = sk::launch<10>(c, p, g, st); break;
+    case 12: rc = sk::launch<12>(c, p, g, st); break;
+    case 16: rc = sk::launch<16>(c, p, g, st); break;
+    case 20: rc = sk::launch<20>(c, p, g, st); break;
+    default: set_error("skinny path: no kernel for BT=%d", g.BT);
   }
-  set_error("skinny path: no kernel for BT=%d", g.BT);
-  return 2;
+  if (rc == 0 && p.dbg) {
+    unsigned long long t[16];
+    MDBN_CUDA(cudaStreamSynchronize(st));
+    MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[skinny timeline us] V=%d H=%d B=%d k=%d:", a.V, a.H, a.B, a.k);
+    for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+  return rc;
 }
 
 }  // namespace mdbn
