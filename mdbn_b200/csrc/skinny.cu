@@ -3,8 +3,13 @@
 // Regime: batch 10-20 on 10^2..2*10^4-wide layers is 0.36*B flop/byte ->
 // bound by streaming W, not by math.  Design:
 //   * every CTA owns a contiguous slab of W rows (visible units) for the whole step;
-//   * W row tiles are staged in shared memory by 1-D bulk async copies (cp.async.bulk ->
-//     UBLKCP) completing on mbarriers, a ring of 16 KB slots;
+//   * W row tiles are staged in shared memory by per-row 1-D bulk async copies
+//     (cp.async.bulk -> UBLKCP) completing on mbarriers; rows are padded in shared memory to a
+//     stride = 24 mod 32 words so the tensor-core fragment loads are bank-conflict free;
+//   * the two skinny GEMMs run on the tensor cores as mma.sync m16n8k8 TF32 with the fp32
+//     operands split hi + lo (3 MMAs per product: hi*hi + lo*hi + hi*lo), which keeps fp32-level
+//     accuracy (the 1e-5 parity bar) at a fraction of the issue slots of FFMA + shuffle
+//     reductions (the tcgen05 shapes, M >= 64, do not fit a 10-20 row batch);
 //   * pass 0      : partial  v0 W          (and round(v0) W for the pseudo-likelihood)
 //   * pass 1..k   : FUSED propdown + propup from the SAME staged tile: v_i = h . W[i,:] is
 //     complete inside the owning CTA (no cross-CTA traffic), its bias/sigmoid/Bernoulli
@@ -25,10 +30,9 @@ namespace sk {
 
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
-constexpr int SLOT = 16384;
-constexpr int MAX_SLOTS = 9;
+constexpr int MAX_SLOTS = 6;
 constexpr int MAX_TR = 64;
-constexpr int DRED_FLOATS = 4096;
+constexpr int MAX_NTD = MAX_TR / 8;
 
 struct Params {
   float *W, *S;
@@ -48,9 +52,9 @@ struct Params {
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
   // geometry
-  int rows_per_cta, n_active, CQ, GW, G, NWG, TR, nslots;
+  int rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, ldp, ldh, slot_bytes;
   // global scratch
-  float* part;        // [n_active][2*BT*ldw]
+  float* part;        // [n_active][2][BT][ldw]
   float *PH, *NH, *HS, *PREX;   // [BT][ldw], zero-initialised, padded columns never written
   float* cost_part;   // [gridDim]
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
@@ -103,75 +107,63 @@ __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long
   __syncthreads();
 }
 
-__host__ __device__ constexpr int half_up(int n) { return (n + 1) / 2; }
-__host__ __device__ constexpr int lvl_size(int n, int l) { return l == 0 ? n : half_up(lvl_size(n, l - 1)); }
-
-// Sum N per-lane values across the 32 lanes by recursive halving: ~N shuffles in total
-// instead of 5N.  Afterwards the lane holds `n` finished sums for indices base..base+n-1.
-template <int N, int L>
-struct HalvingLevel {
-  static __device__ __forceinline__ void run(float (&x)[N], int lane, int& base, int& n) {
-    constexpr int nl = lvl_size(N, L), cnt = half_up(nl), off = 16 >> L;
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < cnt; ++i) {
-      float lo = x[i];
-      float hi = (cnt + i < nl) ? x[cnt + i] : 0.f;
-      float send = upper ? lo : hi;
-      float keep = upper ? hi : lo;
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    if (upper) { base += cnt; n = max(n - cnt, 0); } else { n = min(n, cnt); }
-    if constexpr (L < 4) HalvingLevel<N, L + 1>::run(x, lane, base, n);
-  }
-};
-template <int N>
-__device__ __forceinline__ void warp_halving_sum(float (&x)[N], int lane, int& base, int& n) {
-  base = 0;
-  n = N;
-  HalvingLevel<N, 0>::run(x, lane, base, n);
+// ---- split-TF32 tensor-core helpers -------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
-
-struct Ring {
-  unsigned char* base;
-  uint64_t* bars;
-  uint32_t phase_bits;
-};
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A * B with A = a_hi + a_lo, B = b_hi + b_lo (lo*lo dropped: 2^-22 relative)
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                       uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
 
 template <int BT>
 struct Cfg {
   static constexpr int BTP = (BT + 3) / 4 * 4;
-  static constexpr int R = (BT <= 10) ? 4 : (BT <= 16 ? 2 : 1);   // rows per propdown chunk (register budget)
-  static constexpr int N = R * BT;                  // values per halving reduction
-  static constexpr int NFIN = lvl_size(N, 5);
+  static constexpr int MT = BT > 16 ? 2 : 1;     // 16-row m-tiles of the batch
+  static constexpr int MB = 16 * MT;             // batch rows seen by the MMAs (zero padded)
+  static constexpr int BTS = MT == 1 ? 24 : 40;  // slab row stride in floats, = 8 or 24 mod 32
 };
 
-template <int BT>
+template <int BT, int NPW>
 __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   using C = Cfg<BT>;
-  constexpr int BTP = C::BTP;
+  constexpr int BTP = C::BTP, MT = C::MT, MB = C::MB, BTS = C::BTS;
+  constexpr int NTD = NPW == 16 ? 2 : MAX_NTD;   // wide layers have short tiles (TR <= 16)
+  constexpr bool ALLOW_DUAL = !(NPW == 16 && MT == 2);   // register budget (plan() routes that case away)
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [BT][ldw] chain state
-  float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows][BTP]
-  float* nvs = reinterpret_cast<float*>(smem + p.off_nv);     // [rows][BTP]
-  float* vt = reinterpret_cast<float*>(smem + p.off_vt);      // [TR][BTP] visible tile -> propup input
-  float* dred = reinterpret_cast<float*>(smem + p.off_dred);  // propdown cross-warp partials
+  float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [MB][ldh] chain state
+  float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows_alloc][BTS]
+  float* nvs = reinterpret_cast<float*>(smem + p.off_nv);     // [rows_alloc][BTS]
+  float* vt = reinterpret_cast<float*>(smem + p.off_vt);      // [TR][BTS] visible tile -> propup input
+  float* dred = reinterpret_cast<float*>(smem + p.off_dred);  // [NWARP][MB][TR] propdown k-split partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, pl cost
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lq = lane >> 2, lr = lane & 3;     // mma fragment coordinates
   const int cta = blockIdx.x;
-  const int ldw = p.ldw, ldw4 = ldw >> 2;
+  const int ldw = p.ldw, ldp = p.ldp, ldp4 = ldp >> 2, ldh = p.ldh;
   const int B = p.B, V = p.V, H = p.H;
   const int row0 = cta * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, V - row0));
   const int ntiles = (rows + p.TR - 1) / p.TR;
-  // thread -> (row group g, column quad q)
+  const int ncols8 = (H + 7) & ~7;
+  // SIMT mapping of the statistics pass: thread -> (row group g, column quad q)
   const int q = tid % p.GW, g = tid / p.GW;
-  const bool grp_ok = g < p.G;                 // warp-uniform when GW >= 32
-  const bool col_ok = grp_ok && q < p.CQ;
-  const int wg = (p.GW >= 32) ? (warp % (p.GW >> 5)) : 0;   // warp index inside its group
+  const bool col_ok = g < p.G && q < p.CQ;
   unsigned long long bar_target = 0;
+  uint32_t phase_bits = 0;
   int dbg_i = 0;
   auto mark = [&]() {
     if (p.dbg && cta == 0 && tid == 0) {
@@ -182,31 +174,40 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   };
   mark();
 
-  Ring ring{smem, bars, 0u};
   if (tid == 0) {
     for (int i = 0; i < MAX_SLOTS; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // zero the ring once: the pad columns [ldw, ldp) of every staged row are never written by the
+  // copies and are read (times zero) by the last 8-column fragment
+  for (int e = tid; e < p.nslots * (p.slot_bytes >> 4); e += NT)
+    reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = tid; e < MB * ldh; e += NT) hs[e] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  // ---- tile pipeline helpers -------------------------------------------------
-  // job j of a pass loads `narr` arrays (W [, S [, Wsnap]]) of tile j into consecutive slots.
-  auto issue = [&](int j, int narr, int depth) {      // thread 0 only; jobs are issued in order j = 0,1,2,...
+  // ---- tile pipeline --------------------------------------------------------------
+  // job j of a pass loads `narr` arrays (W [, S [, Wsnap]]) of tile j into consecutive slots, one
+  // bulk copy per row (padded destination stride).  Called by all lanes of warp 0.
+  auto issue = [&](int j, int narr, int depth) {
     if (j >= ntiles) return;
-    int st = j % depth;
-    int r0 = j * p.TR, nr = min(p.TR, rows - r0);
-    uint32_t bytes = (uint32_t)nr * ldw * 4u;
-    uint64_t* bar = &ring.bars[st];
-    mbar_expect_tx(bar, bytes * narr);
-    size_t goff = (size_t)(row0 + r0) * ldw;
-    unsigned char* dst = ring.base + (size_t)st * narr * SLOT;
-    bulk_g2s(dst, p.W + goff, bytes, bar);
-    if (narr > 1) bulk_g2s(dst + SLOT, p.S + goff, bytes, bar);
-    if (narr > 2) bulk_g2s(dst + 2 * SLOT, p.Wsnap + goff, bytes, bar);
+    const int st = j % depth;
+    const int r0 = j * p.TR, nr = min(p.TR, rows - r0);
+    const uint32_t rbytes = (uint32_t)ldw * 4u;
+    uint64_t* bar = &bars[st];
+    if (lane == 0) mbar_expect_tx(bar, rbytes * nr * narr);
+    __syncwarp();
+    unsigned char* dst = smem + (size_t)st * narr * p.slot_bytes;
+    for (int r = lane; r < nr; r += 32) {
+      const size_t goff = (size_t)(row0 + r0 + r) * ldw;
+      bulk_g2s(dst + (size_t)r * ldp * 4, p.W + goff, rbytes, bar);
+      if (narr > 1) bulk_g2s(dst + p.slot_bytes + (size_t)r * ldp * 4, p.S + goff, rbytes, bar);
+      if (narr > 2) bulk_g2s(dst + 2 * (size_t)p.slot_bytes + (size_t)r * ldp * 4, p.Wsnap + goff, rbytes, bar);
+    }
   };
   auto wait_stage = [&](int st) {
-    mbar_wait(&ring.bars[st], (ring.phase_bits >> st) & 1u);
-    ring.phase_bits ^= (1u << st);
+    mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+    phase_bits ^= (1u << st);
   };
 
   // ---- randomness -------------------------------------------------------------
@@ -218,95 +219,85 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     return s;
   };
 
-  // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r] ---------------------------
-  for (int e = tid; e < rows * BTP; e += NT) {
-    int b = e / rows, r = e % rows;
+  // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
+  if (warp == 0) issue(0, 1, p.nslots);     // start streaming W while the minibatch is gathered
+  for (int e = tid; e < p.rows_alloc * MB; e += NT) {
+    int b = e / p.rows_alloc, r = e % p.rows_alloc;
     float x = 0.f;
-    if (b < B) {
+    if (b < B && r < rows) {
       long long dr = p.idx ? p.idx[b] : b;
       x = p.data[dr * p.ld_data + row0 + r];
     }
-    v0s[r * BTP + b] = x;
-    if (p.pcd) nvs[r * BTP + b] = roundf(x);   // src/rbm.py:428; slab is free until the last Gibbs step
+    v0s[r * BTS + b] = x;
+    nvs[r * BTS + b] = p.pcd ? roundf(x) : 0.f;   // src/rbm.py:428; slab is free until the last Gibbs step
   }
   __syncthreads();
+  mark();   // gather done
 
-  // ---- propup accumulation of one staged tile: acc[b] += src[r][b] * W[r, 4q..4q+3] -------
-  // DUAL: a second input slab (round(v0), pseudo-likelihood) shares the W loads.
-  auto up_tile = [&](const float4* __restrict__ tile, const float* __restrict__ src, const float* __restrict__ src2,
-                     int nr, float4 (&acc)[BT], float4 (&acc2)[BT], bool dual) {
-    if (!col_ok) return;
-    for (int r = g; r < nr; r += p.G) {
-      float4 w = tile[r * ldw4 + q];
-      const float4* vr = reinterpret_cast<const float4*>(src + r * BTP);
+  // ---- propup of one staged tile on the tensor cores ------------------------------------
+  // out[b, j] += sum_i src[i][b] * W[i][j]; warp w owns the 8-column n-tiles w, w+8, ...;
+  // DUAL shares the W fragments with a second input slab.
+  auto up_mma = [&](const float* __restrict__ tile, const float* __restrict__ src, const float* __restrict__ src2,
+                    int nr8, float (&acc)[MT][NPW][4], float (&acc2)[MT][NPW][4], bool dual) {
+    for (int i0 = 0; i0 < nr8; i0 += 8) {
+      uint32_t ah[MT][4], al[MT][4], a2h[MT][4], a2l[MT][4];
 #pragma unroll
-      for (int b4 = 0; b4 < BTP / 4; ++b4) {
-        float4 vv = vr[b4];
-        float xs[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int b = b4 * 4 + t;
-          if (b < BT) {
-            acc[b].x = fmaf(xs[t], w.x, acc[b].x);
-            acc[b].y = fmaf(xs[t], w.y, acc[b].y);
-            acc[b].z = fmaf(xs[t], w.z, acc[b].z);
-            acc[b].w = fmaf(xs[t], w.w, acc[b].w);
-          }
+      for (int mt = 0; mt < MT; ++mt) {
+        const float* s0 = src + (i0 + lr) * BTS + mt * 16 + lq;
+        split_tf32(s0[0], ah[mt][0], al[mt][0]);
+        split_tf32(s0[8], ah[mt][1], al[mt][1]);
+        split_tf32(s0[4 * BTS], ah[mt][2], al[mt][2]);
+        split_tf32(s0[4 * BTS + 8], ah[mt][3], al[mt][3]);
+        if (dual) {
+          const float* t0 = src2 + (i0 + lr) * BTS + mt * 16 + lq;
+          split_tf32(t0[0], a2h[mt][0], a2l[mt][0]);
+          split_tf32(t0[8], a2h[mt][1], a2l[mt][1]);
+          split_tf32(t0[4 * BTS], a2h[mt][2], a2l[mt][2]);
+          split_tf32(t0[4 * BTS + 8], a2h[mt][3], a2l[mt][3]);
         }
       }
-      if (dual) {
-        const float4* xr = reinterpret_cast<const float4*>(src2 + r * BTP);
 #pragma unroll
-        for (int b4 = 0; b4 < BTP / 4; ++b4) {
-          float4 vv = xr[b4];
-          float xs[4] = {vv.x, vv.y, vv.z, vv.w};
+      for (int nt = 0; nt < NPW; ++nt) {
+        const int n0 = (warp + nt * NWARP) * 8;
+        if (n0 < ncols8) {
+          const float* w0 = tile + (i0 + lr) * ldp + n0 + lq;
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(w0[0], bh0, bl0);
+          split_tf32(w0[4 * ldp], bh1, bl1);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int b = b4 * 4 + t;
-            if (b < BT) {
-              acc2[b].x = fmaf(xs[t], w.x, acc2[b].x);
-              acc2[b].y = fmaf(xs[t], w.y, acc2[b].y);
-              acc2[b].z = fmaf(xs[t], w.z, acc2[b].z);
-              acc2[b].w = fmaf(xs[t], w.w, acc2[b].w);
-            }
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_3x(acc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+            if (dual) mma_3x(acc2[mt][nt], a2h[mt], a2l[mt], bh0, bh1, bl0, bl1);
           }
         }
       }
     }
   };
 
-  // ---- CTA partial [BT][ldw]: sum over the G row groups (fixed order), then to global scratch ---
-  // uses hs as the staging accumulator (it is reloaded after the reduction anyway)
-  auto flush_partial = [&](float4 (&acc)[BT], int set) {
-    float4* stage = reinterpret_cast<float4*>(hs);
-    for (int gg = 0; gg < p.G; ++gg) {
-      if (col_ok && g == gg) {
+  // ---- this CTA's partial [BT][ldw] straight from the accumulator fragments to global scratch ----
+  auto flush_partial = [&](float (&acc)[MT][NPW][4], int set) {
+    if (rows <= 0) return;
+    float* dst = p.part + ((size_t)cta * 2 + set) * BT * ldw;
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          float4 a = acc[b];
-          if (gg > 0) {
-            float4 o = stage[b * ldw4 + q];
-            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-          }
-          stage[b * ldw4 + q] = a;
+    for (int nt = 0; nt < NPW; ++nt) {
+      const int j = (warp + nt * NWARP) * 8 + 2 * lr;
+      if (j < ldw) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int b = mt * 16 + lq;
+          if (b < BT) __stcg(reinterpret_cast<float2*>(dst + b * ldw + j), make_float2(acc[mt][nt][0], acc[mt][nt][1]));
+          if (b + 8 < BT)
+            __stcg(reinterpret_cast<float2*>(dst + (b + 8) * ldw + j), make_float2(acc[mt][nt][2], acc[mt][nt][3]));
         }
       }
-      __syncthreads();
     }
-    if (rows > 0) {
-      float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)cta * 2 + set) * BT * ldw);
-      for (int e = tid; e < BT * p.CQ; e += NT) {
-        int b = e / p.CQ, qq = e % p.CQ;
-        __stcg(&dst[b * ldw4 + qq], stage[b * ldw4 + qq]);
-      }
-    }
-    __syncthreads();
   };
 
   // ---- distributed reduction of the hidden pre-activations + epilogue ----------------
   //  set 0: pre = sum + hb -> mean (sigmoid) -> mean_out, sample -> HS (and P on the last PCD step)
   //  set 1: PREX = sum + hb (pre-activation of round(v0), pseudo-likelihood)
   auto reduce_hidden = [&](int nsets, float* mean_out, const RngSeg& rs, bool write_hs, bool write_p) {
+    const int ldw4 = ldw >> 2;
     const int nq = nsets * BT * p.CQ;
     const int per = (nq + gridDim.x - 1) / gridDim.x;
     const int o0 = cta * per, o1 = min(nq, o0 + per);
@@ -353,30 +344,33 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       int b = e / ldw, j = e % ldw;
       float x = 0.f;
       if (b < nrows_src && j < H) x = __ldcg(&src[(size_t)b * ld_src + j]);
-      hs[e] = x;
+      hs[b * ldh + j] = x;
     }
     __syncthreads();
   };
 
-  mark();   // gather done
   // =============================== pass 0: positive phase ===============================
   {
     const int depth = p.nslots;
-    if (tid == 0) for (int j = 0; j < depth; ++j) issue(j, 1, depth);
-    float4 acc[BT], acc2[BT];
+    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth);
+    float acc[MT][NPW][4], acc2[MT][NPW][4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = acc2[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NPW; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mt][nt][c] = acc2[mt][nt][c] = 0.f;
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
       wait_stage(st);
-      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)st * SLOT);
-      int nr = min(p.TR, rows - j * p.TR);
-      up_tile(tile, v0s + (size_t)j * p.TR * BTP, nvs + (size_t)j * p.TR * BTP, nr, acc, acc2, p.pcd != 0);
+      const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
+      const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7;
+      up_mma(tile, v0s + (size_t)j * p.TR * BTS, nvs + (size_t)j * p.TR * BTS, nr8, acc, acc2, ALLOW_DUAL && p.pcd != 0);
       __syncthreads();
-      if (tid == 0) issue(j + depth, 1, depth);
+      if (warp == 0) issue(j + depth, 1, depth);
     }
     mark();   // pass-0 tiles done
     flush_partial(acc, 0);
-    if (p.pcd) flush_partial(acc2, 1);
+    if (ALLOW_DUAL && p.pcd) flush_partial(acc2, 1);
   }
   mark();
   grid_sync(p.bar, bar_target);
@@ -385,6 +379,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   reduce_hidden(p.pcd ? 2 : 1, p.PH, seg(0, 0), !p.pcd, false);
   mark();   // reduce 0 done
   grid_sync(p.bar, bar_target);
+  if (warp == 0) issue(0, 1, p.nslots);     // W is unchanged until the update: prefetch the next pass now
   if (p.pcd) load_hs(p.P, H, B); else load_hs(p.HS, ldw, BT);
   mark();
 
@@ -427,70 +422,73 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s);
     const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s);
     const int depth = p.nslots;
-    if (tid == 0) for (int j = 0; j < depth; ++j) issue(j, 1, depth);
-    // chain state of this thread's columns
-    float4 hreg[BT];
+    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth);   // job 0 was prefetched
+    float acc[MT][NPW][4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b)
-      hreg[b] = col_ok ? reinterpret_cast<const float4*>(hs)[b * ldw4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc[BT];
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int nt = 0; nt < NPW; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
 
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
       wait_stage(st);
-      const float4* tile = reinterpret_cast<const float4*>(ring.base + (size_t)st * SLOT);
-      const int nr = min(p.TR, rows - j * p.TR);
-      // ---- propdown of the tile rows: partial dot over this thread's 4 columns, then across lanes
-      if (grp_ok) {
-        // uniform trip count for every lane: the reductions below are warp-synchronous
-        for (int rb0 = 0; rb0 < nr; rb0 += p.G * C::R) {
-          const int rb = rb0 + g * C::R;
-          float x[C::N];
+      const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
+      const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7, ntd = nr8 >> 3;
+      // ---- propdown of the tile rows: out[b, i] = sum_j h[b][j] W[i][j]; the 8 warps split j ----
+      {
+        float dacc[MT][NTD][4];
 #pragma unroll
-          for (int rr = 0; rr < C::R; ++rr) {
-            int r = rb + rr;
-            float4 w = (col_ok && r < nr) ? tile[r * ldw4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int b = 0; b < BT; ++b)
-              x[rr * BT + b] = fmaf(hreg[b].x, w.x, fmaf(hreg[b].y, w.y, fmaf(hreg[b].z, w.z, hreg[b].w * w.w)));
+          for (int nt = 0; nt < NTD; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dacc[mt][nt][c] = 0.f;
+        for (int j0 = warp * 8; j0 < ncols8; j0 += NWARP * 8) {
+          uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const float* h0 = hs + (mt * 16 + lq) * ldh + j0 + lr;
+            split_tf32(h0[0], ah[mt][0], al[mt][0]);
+            split_tf32(h0[8 * ldh], ah[mt][1], al[mt][1]);
+            split_tf32(h0[4], ah[mt][2], al[mt][2]);
+            split_tf32(h0[8 * ldh + 4], ah[mt][3], al[mt][3]);
           }
-          if (p.GW >= 32) {
-            int base, n;
-            warp_halving_sum<C::N>(x, lane, base, n);
 #pragma unroll
-            for (int t = 0; t < C::NFIN; ++t) {
-              if (t < n) {
-                int id = base + t, rr = id / BT, b = id % BT, r = rb + rr;
-                if (r < nr) dred[(r * BT + b) * p.NWG + wg] = x[t];
-              }
+          for (int nt = 0; nt < NTD; ++nt) {
+            if (nt < ntd) {
+              const float* w0 = tile + (nt * 8 + lq) * ldp + j0 + lr;
+              uint32_t bh0, bl0, bh1, bl1;
+              split_tf32(w0[0], bh0, bl0);
+              split_tf32(w0[4], bh1, bl1);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) mma_3x(dacc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
             }
-          } else {
-            // narrow layers: several row groups share a warp -> butterfly inside the GW lanes
-            for (int off = p.GW >> 1; off > 0; off >>= 1) {
+          }
+        }
 #pragma unroll
-              for (int i = 0; i < C::N; ++i) x[i] += __shfl_xor_sync(0xffffffffu, x[i], off);
-            }
-            if (q == 0) {
+        for (int nt = 0; nt < NTD; ++nt) {
+          if (nt < ntd) {
 #pragma unroll
-              for (int i = 0; i < C::N; ++i) {
-                int rr = i / BT, b = i % BT, r = rb + rr;
-                if (r < nr) dred[(r * BT + b)] = x[i];
-              }
+            for (int mt = 0; mt < MT; ++mt) {
+              float* d0 = dred + ((size_t)warp * MB + mt * 16 + lq) * p.TR + nt * 8 + 2 * lr;
+              *reinterpret_cast<float2*>(d0) = make_float2(dacc[mt][nt][0], dacc[mt][nt][1]);
+              *reinterpret_cast<float2*>(d0 + 8 * p.TR) = make_float2(dacc[mt][nt][2], dacc[mt][nt][3]);
             }
           }
         }
       }
       __syncthreads();
       // ---- visible epilogue: bias, activation, sampling (src/rbm.py:226-240 / :650-660) ----
-      for (int it = tid; it < nr * BT; it += NT) {
-        int r = it / BT, b = it % BT;
-        float sum = 0.f;
-        for (int w2 = 0; w2 < p.NWG; ++w2) sum += dred[it * p.NWG + w2];
-        int gi = row0 + j * p.TR + r;
-        float pre = sum + p.vb[gi];
-        float mean = 0.f, vin = 0.f;
-        if (b < B) {
+      for (int it = tid; it < nr8 * MB; it += NT) {
+        const int r = it / MB, b = it % MB;
+        float vin = 0.f, mean = 0.f;
+        if (r < nr && b < B) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < NWARP; ++w2) sum += dred[((size_t)w2 * MB + b) * p.TR + r];
+          const int gi = row0 + j * p.TR + r;
+          const float pre = sum + p.vb[gi];
           if (p.kind == MDBN_GRBM) {
             mean = pre;
             vin = pre;        // mean-field visible: h given v_MEAN (src/rbm.py:669)
@@ -499,27 +497,19 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
             vin = rng_uniform(rs_v, (long long)b * V + gi) < mean ? 1.f : 0.f;
           }
           if (last && !p.pcd) {
-            float t = v0s[(j * p.TR + r) * BTP + b];
+            const float t = v0s[(j * p.TR + r) * BTS + b];
             if (p.kind == MDBN_GRBM) { float d = sigmoidf_(pre) - t; cost_acc += d * d; }   // :697
             else cost_acc += t * softplusf_(-pre) + (1.f - t) * softplusf_(pre);          // :479-480
           }
         }
-        vt[r * BTP + b] = vin;
-        if (last) nvs[(j * p.TR + r) * BTP + b] = mean;
-      }
-      if constexpr (BTP > BT) {
-        constexpr int PADB = BTP - BT;
-        for (int it = tid; it < nr * PADB; it += NT) {
-          int r = it / PADB, b = BT + it % PADB;
-          vt[r * BTP + b] = 0.f;
-          if (last) nvs[(j * p.TR + r) * BTP + b] = 0.f;
-        }
+        vt[r * BTS + b] = vin;
+        if (last) nvs[(j * p.TR + r) * BTS + b] = mean;
       }
       __syncthreads();
       // ---- propup accumulation from the same tile ----
-      up_tile(tile, vt, vt, nr, acc, acc, false);
+      up_mma(tile, vt, vt, nr8, acc, acc, false);
       __syncthreads();
-      if (tid == 0) issue(j + depth, 1, depth);
+      if (warp == 0) issue(j + depth, 1, depth);
     }
     if (last) mark();   // Gibbs tiles done
     flush_partial(acc, 0);
@@ -532,14 +522,18 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     reduce_hidden(1, p.NH, rs_h, !last, last && p.pcd);
     grid_sync(p.bar, bar_target);
     if (last) mark();
-    if (!last) load_hs(p.HS, ldw, BT);
+    if (!last) {
+      if (warp == 0) issue(0, 1, p.nslots);
+      load_hs(p.HS, ldw, BT);
+    }
   }
 
   // =============================== statistics + update ===============================
   {
     const int narr = p.wc != 0.f ? 3 : 2;
     const int depth = p.nslots / narr;
-    if (tid == 0) for (int j = 0; j < depth; ++j) issue(j, narr, depth);
+    if (warp == 0) for (int j = 0; j < depth; ++j) issue(j, narr, depth);
+    const int ldw4 = ldw >> 2;
     float4 ph[BT], nh[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
@@ -553,17 +547,17 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     const int ncol = min(4, H - 4 * q);
     for (int j = 0, stg = 0; j < ntiles; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
       wait_stage(stg);
-      const unsigned char* sb = ring.base + (size_t)stg * narr * SLOT;
+      const unsigned char* sb = smem + (size_t)stg * narr * p.slot_bytes;
       const float4* wt = reinterpret_cast<const float4*>(sb);
-      const float4* st = reinterpret_cast<const float4*>(sb + SLOT);
-      const float4* sn = reinterpret_cast<const float4*>(sb + 2 * SLOT);
+      const float4* st = reinterpret_cast<const float4*>(sb + p.slot_bytes);
+      const float4* sn = reinterpret_cast<const float4*>(sb + 2 * (size_t)p.slot_bytes);
       const int nr = min(p.TR, rows - j * p.TR);
       if (col_ok) {
         for (int r = g; r < nr; r += p.G) {
           const int lr_ = j * p.TR + r;
-          float4 w = wt[r * ldw4 + q], sp = st[r * ldw4 + q];
-          const float4* a4 = reinterpret_cast<const float4*>(v0s + lr_ * BTP);
-          const float4* n4 = reinterpret_cast<const float4*>(nvs + lr_ * BTP);
+          float4 w = wt[r * ldp4 + q], sp = st[r * ldp4 + q];
+          const float4* a4 = reinterpret_cast<const float4*>(v0s + lr_ * BTS);
+          const float4* n4 = reinterpret_cast<const float4*>(nvs + lr_ * BTS);
           float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int b4 = 0; b4 < BTP / 4; ++b4) {
@@ -582,7 +576,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
           }
           float wv[4] = {w.x, w.y, w.z, w.w}, sv[4] = {sp.x, sp.y, sp.z, sp.w}, gv[4] = {gs.x, gs.y, gs.z, gs.w};
           float snv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (narr > 2) { float4 t4 = sn[r * ldw4 + q]; snv[0] = t4.x; snv[1] = t4.y; snv[2] = t4.z; snv[3] = t4.w; }
+          if (narr > 2) { float4 t4 = sn[r * ldp4 + q]; snv[0] = t4.x; snv[1] = t4.y; snv[2] = t4.z; snv[3] = t4.w; }
           float wo[4], so[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -609,12 +603,12 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         }
       }
       __syncthreads();
-      if (tid == 0) issue(j + depth, narr, depth);
+      if (warp == 0) issue(j + depth, narr, depth);
     }
     // visible bias (rows owned by this CTA)  src/rbm.py:417
     for (int r = tid; r < rows; r += NT) {
       float gsum = 0.f;
-      for (int b = 0; b < B; ++b) gsum += v0s[r * BTP + b] - nvs[r * BTP + b];
+      for (int b = 0; b < B; ++b) gsum += v0s[r * BTS + b] - nvs[r * BTS + b];
       float gb = gsum * p.inv_b, sv = p.Svb[row0 + r];
       p.Svb[row0 + r] = gb + (sv - gb) * p.mom;
       p.vb[row0 + r] = p.vb[row0 + r] + sv * p.lr;
@@ -658,58 +652,62 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 }
 
 struct Geometry {
-  int BT, rows_per_cta, n_active, CQ, GW, G, NWG, TR, nslots, grid;
+  int BT, NPW, rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, grid, ldp, ldh, slot_bytes;
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc;
   size_t smem;
   bool ok;
 };
 
-static int pick_bt(int B) {
-  const int opts[] = {4, 8, 10, 12, 16, 20};
-  for (int o : opts)
-    if (B <= o) return o;
-  return 0;
-}
+static int pad_mod32(int n, int want) { return n + ((want - n % 32) + 32) % 32; }
 
 static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   Geometry g{};
   g.ok = false;
-  g.BT = pick_bt(a.B);
+  g.BT = a.B <= 10 ? 10 : (a.B <= 20 ? 20 : 0);
   if (!g.BT || a.ldw % 4 != 0) return g;
   if (((uintptr_t)a.W | (uintptr_t)a.W_speed | (uintptr_t)a.W_snap) & 15) return g;
-  const int BTP = (g.BT + 3) / 4 * 4;
+  const int MT = g.BT > 16 ? 2 : 1, MB = 16 * MT, BTS = MT == 1 ? 24 : 40;
+  const bool pcd = a.persistent != nullptr;
   g.CQ = a.ldw / 4;
   if (g.CQ > NT) return g;
+  const int ncols8 = (a.H + 7) & ~7;
+  g.NPW = ncols8 <= 512 ? 8 : 16;
+  if (ncols8 > 1024) return g;
+  if (g.NPW == 16 && MT == 2 && pcd) return g;     // register budget of the dual accumulators
   if (g.CQ <= 32) { g.GW = 1; while (g.GW < g.CQ) g.GW <<= 1; } else g.GW = (g.CQ + 31) / 32 * 32;
   g.G = NT / g.GW;
-  g.NWG = g.GW >= 32 ? g.GW / 32 : 1;
   g.grid = c->num_sms;
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
+  g.rows_alloc = (g.rows_per_cta + 7) & ~7;
   g.n_active = (a.V + g.rows_per_cta - 1) / g.rows_per_cta;
-  int tr = SLOT / (a.ldw * 4);
-  if (tr < 1) return g;
-  g.TR = tr > MAX_TR ? MAX_TR : tr;
-  if (g.TR * g.BT * g.NWG > DRED_FLOATS) g.TR = DRED_FLOATS / (g.BT * g.NWG);
-  if (g.TR < 1) return g;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) & ~(size_t)127; return (int)o; };
-  size_t fixed_after_ring;
-  // ring first (1024-aligned), sized last: compute the fixed part, then give the ring what is left
-  size_t hs_b = (size_t)g.BT * a.ldw * 4, slab_b = (size_t)g.rows_per_cta * BTP * 4, vt_b = (size_t)MAX_TR * BTP * 4;
-  fixed_after_ring = ((hs_b + 127) & ~127) + 2 * ((slab_b + 127) & ~127) + ((vt_b + 127) & ~127) +
-                     DRED_FLOATS * 4 + 128 + 256 + 1024;
+  g.ldp = pad_mod32(a.ldw > ncols8 ? a.ldw : ncols8, 24);
+  g.ldh = pad_mod32(ncols8, 20);
+  int tr = (40 * 1024) / (g.ldp * 4);
+  tr &= ~7;
+  if (tr < 8) return g;
+  if (tr > MAX_TR) tr = MAX_TR;
+  if (g.NPW == 16 && tr > 16) tr = 16;
+  // no point in tiles taller than the slab
+  while (tr > 8 && tr - 8 >= g.rows_alloc) tr -= 8;
+  g.TR = tr;
+  g.slot_bytes = (g.TR * g.ldp * 4 + 127) & ~127;
+  auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
+  const size_t hs_b = up128((size_t)MB * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
+               vt_b = up128((size_t)MAX_TR * BTS * 4), dred_b = up128((size_t)NWARP * MB * g.TR * 4);
+  const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256;
   const size_t smem_max = 227 * 1024;
-  if (fixed_after_ring + 4 * SLOT > smem_max) return g;
-  g.nslots = (int)((smem_max - fixed_after_ring) / SLOT);
-  if (g.nslots > MAX_SLOTS) g.nslots = MAX_SLOTS;
   const int narr = a.weightcost != 0.f ? 3 : 2;
-  if (g.nslots < narr) return g;
-  off = (size_t)g.nslots * SLOT;
+  if (fixed + (size_t)narr * g.slot_bytes > smem_max) return g;
+  g.nslots = (int)((smem_max - fixed) / g.slot_bytes);
+  if (g.nslots > MAX_SLOTS) g.nslots = MAX_SLOTS;
+  if (g.nslots < narr || g.nslots < 2) return g;
+  size_t off = (size_t)g.nslots * g.slot_bytes;
+  auto take = [&](size_t bytes) { size_t o = off; off += bytes; return (int)o; };
   g.off_hs = take(hs_b);
   g.off_v0 = take(slab_b);
   g.off_nv = take(slab_b);
   g.off_vt = take(vt_b);
-  g.off_dred = take(DRED_FLOATS * 4);
+  g.off_dred = take(dred_b);
   g.off_bars = take(128);
   g.off_misc = take(256);
   g.smem = off;
@@ -717,10 +715,10 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   return g;
 }
 
-template <int BT>
+template <int BT, int NPW>
 static int launch(mdbn_ctx* c, const Params& p, const Geometry& g, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kfn = cd_skinny_kernel<BT>;
+  auto kfn = cd_skinny_kernel<BT, NPW>;
   if (!configured[c->device]) {
     MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[c->device] = true;
@@ -735,7 +733,6 @@ static int launch(mdbn_ctx* c, const Params& p, const Geometry& g, cudaStream_t 
 
 bool skinny_supported(const mdbn_ctx* c, const mdbn_cd_args& a) {
   if (a.phase != MDBN_PHASE_FULL) return false;
-  if (a.persistent && a.B != a.B_nom && false) return false;
   return sk::plan(c, a).ok;
 }
 
@@ -761,8 +758,9 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.c2 = (uint32_t)a.rng.offset; p.c3 = (uint32_t)(a.rng.offset >> 32);
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
-  p.rows_per_cta = g.rows_per_cta; p.n_active = g.n_active; p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.NWG = g.NWG;
-  p.TR = g.TR; p.nslots = g.nslots;
+  p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.n_active = g.n_active;
+  p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.TR = g.TR; p.nslots = g.nslots;
+  p.ldp = g.ldp; p.ldh = g.ldh; p.slot_bytes = g.slot_bytes;
   p.off_hs = g.off_hs; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vt = g.off_vt; p.off_dred = g.off_dred;
   p.off_bars = g.off_bars; p.off_misc = g.off_misc;
 
@@ -794,15 +792,11 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
   p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;
   int rc = 2;
-  switch (g.BT) {
-    case 4: rc = sk::launch<4>(c, p, g, st); break;
-    case 8: rc = sk::launch<8>(c, p, g, st); break;
-    case 10: rc = sk::launch<10>(c, p, g, st); break;
-    case 12: rc = sk::launch<12>(c, p, g, st); break;
-    case 16: rc = sk::launch<16>(c, p, g, st); break;
-    case 20: rc = sk::launch<20>(c, p, g, st); break;
-    default: set_error("skinny path: no kernel for BT=%d", g.BT);
-  }
+  if (g.BT == 10 && g.NPW == 8) rc = sk::launch<10, 8>(c, p, g, st);
+  else if (g.BT == 10 && g.NPW == 16) rc = sk::launch<10, 16>(c, p, g, st);
+  else if (g.BT == 20 && g.NPW == 8) rc = sk::launch<20, 8>(c, p, g, st);
+  else if (g.BT == 20 && g.NPW == 16) rc = sk::launch<20, 16>(c, p, g, st);
+  else set_error("skinny path: no kernel for BT=%d NPW=%d", g.BT, g.NPW);
   if (rc == 0 && p.dbg) {
     unsigned long long t[16];
     MDBN_CUDA(cudaStreamSynchronize(st));
