@@ -3,9 +3,9 @@
 // Regime: batch 10-20 on 10^2..2*10^4-wide layers is 0.36*B flop/byte ->
 // bound by streaming W, not by math.  Design:
 //   * every CTA owns a contiguous slab of W rows (visible units) for the whole step;
-//   * W row tiles are staged in shared memory by per-row 1-D bulk async copies
-//     (cp.async.bulk -> UBLKCP) completing on mbarriers; rows are padded in shared memory to a
-//     stride = 24 mod 32 words so the tensor-core fragment loads are bank-conflict free;
+//   * W row tiles are staged in shared memory by 1-D bulk async copies
+//     (cp.async.bulk -> UBLKCP, one per tile: the TMA op rate, ~150 ns per copy per SM, rules
+//     out per-row copies) completing on mbarriers;
 //   * the two skinny GEMMs run on the tensor cores as mma.sync m16n8k8 TF32 with the fp32
 //     operands split hi + lo (3 MMAs per product: hi*hi + lo*hi + hi*lo), which keeps fp32-level
 //     accuracy (the 1e-5 parity bar) at a fraction of the issue slots of FFMA + shuffle
@@ -31,7 +31,7 @@ namespace sk {
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 constexpr int MAX_SLOTS = 6;
-constexpr int MAX_TR = 64;
+constexpr int MAX_TR = 32;
 constexpr int MAX_NTD = MAX_TR / 8;
 
 struct Params {
@@ -109,12 +109,14 @@ __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long
 
 // ---- split-TF32 tensor-core helpers -------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  // hi = x truncated to tf32 (what the tensor core would do anyway), lo = exact remainder, itself
+  // truncated by the hardware: |x - hi - tf32(lo)| <= 2^-21 |x|.  Bit masks, not cvt.rna: the
+  // conversions run on the quarter-rate XU pipe and were the bottleneck of this loop.
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -164,7 +166,14 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   const bool col_ok = g < p.G && q < p.CQ;
   unsigned long long bar_target = 0;
   uint32_t phase_bits = 0;
-  int dbg_i = 0;
+  int dbg_i = 0, dbg_j = 16;
+  auto mark2 = [&]() {
+    if (p.dbg && cta == 0 && tid == 0 && dbg_j < 32) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[dbg_j++] = t;
+    }
+  };
   auto mark = [&]() {
     if (p.dbg && cta == 0 && tid == 0) {
       unsigned long long t;
@@ -189,21 +198,19 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   // ---- tile pipeline --------------------------------------------------------------
   // job j of a pass loads `narr` arrays (W [, S [, Wsnap]]) of tile j into consecutive slots, one
   // bulk copy per row (padded destination stride).  Called by all lanes of warp 0.
-  auto issue = [&](int j, int narr, int depth) {
-    if (j >= ntiles) return;
+  auto issue = [&](int j, int narr, int depth, int tr, int slot_b) {      // lane 0 of warp 0
+    const int r0 = j * tr;
+    if (r0 >= rows || lane != 0) return;
     const int st = j % depth;
-    const int r0 = j * p.TR, nr = min(p.TR, rows - r0);
-    const uint32_t rbytes = (uint32_t)ldw * 4u;
+    const int nr = min(tr, rows - r0);
+    const uint32_t bytes = (uint32_t)nr * ldw * 4u;       // rows are contiguous: ONE bulk copy per array
     uint64_t* bar = &bars[st];
-    if (lane == 0) mbar_expect_tx(bar, rbytes * nr * narr);
-    __syncwarp();
-    unsigned char* dst = smem + (size_t)st * narr * p.slot_bytes;
-    for (int r = lane; r < nr; r += 32) {
-      const size_t goff = (size_t)(row0 + r0 + r) * ldw;
-      bulk_g2s(dst + (size_t)r * ldp * 4, p.W + goff, rbytes, bar);
-      if (narr > 1) bulk_g2s(dst + p.slot_bytes + (size_t)r * ldp * 4, p.S + goff, rbytes, bar);
-      if (narr > 2) bulk_g2s(dst + 2 * (size_t)p.slot_bytes + (size_t)r * ldp * 4, p.Wsnap + goff, rbytes, bar);
-    }
+    mbar_expect_tx(bar, bytes * narr);
+    unsigned char* dst = smem + (size_t)st * narr * slot_b;
+    const size_t goff = (size_t)(row0 + r0) * ldw;
+    bulk_g2s(dst, p.W + goff, bytes, bar);
+    if (narr > 1) bulk_g2s(dst + slot_b, p.S + goff, bytes, bar);
+    if (narr > 2) bulk_g2s(dst + 2 * (size_t)slot_b, p.Wsnap + goff, bytes, bar);
   };
   auto wait_stage = [&](int st) {
     mbar_wait(&bars[st], (phase_bits >> st) & 1u);
@@ -220,7 +227,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   };
 
   // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
-  if (warp == 0) issue(0, 1, p.nslots);     // start streaming W while the minibatch is gathered
+  if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);     // start streaming W while the minibatch is gathered
+  int exact_pred = 1, exact_pred2 = 1;
   for (int e = tid; e < p.rows_alloc * MB; e += NT) {
     int b = e / p.rows_alloc, r = e % p.rows_alloc;
     float x = 0.f;
@@ -228,17 +236,22 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       long long dr = p.idx ? p.idx[b] : b;
       x = p.data[dr * p.ld_data + row0 + r];
     }
+    const float xr = p.pcd ? roundf(x) : 0.f;     // src/rbm.py:428; the nv slab is free until the last Gibbs step
     v0s[r * BTS + b] = x;
-    nvs[r * BTS + b] = p.pcd ? roundf(x) : 0.f;   // src/rbm.py:428; slab is free until the last Gibbs step
+    nvs[r * BTS + b] = xr;
+    exact_pred &= ((__float_as_uint(x) & 0x1FFFu) == 0u) ? 1 : 0;       // representable in tf32?
+    exact_pred2 &= ((__float_as_uint(xr) & 0x1FFFu) == 0u) ? 1 : 0;
   }
-  __syncthreads();
+  const bool v0_exact = __syncthreads_and(exact_pred) != 0;    // binary / small-integer data: no low term
+  const bool x_exact = __syncthreads_and(exact_pred2) != 0;
   mark();   // gather done
 
   // ---- propup of one staged tile on the tensor cores ------------------------------------
   // out[b, j] += sum_i src[i][b] * W[i][j]; warp w owns the 8-column n-tiles w, w+8, ...;
   // DUAL shares the W fragments with a second input slab.
   auto up_mma = [&](const float* __restrict__ tile, const float* __restrict__ src, const float* __restrict__ src2,
-                    int nr8, float (&acc)[MT][NPW][4], float (&acc2)[MT][NPW][4], bool dual) {
+                    int nr8, float (&acc)[MT][NPW][4], float (&acc2)[MT][NPW][4], bool dual, bool a_exact,
+                    bool a2_exact) {
     for (int i0 = 0; i0 < nr8; i0 += 8) {
       uint32_t ah[MT][4], al[MT][4], a2h[MT][4], a2l[MT][4];
 #pragma unroll
@@ -256,18 +269,36 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
           split_tf32(t0[4 * BTS + 8], a2h[mt][3], a2l[mt][3]);
         }
       }
+      // B fragments of all n-tiles first, then the three split terms term-major so that
+      // back-to-back MMAs never hit the same accumulator (dependent-issue latency)
+      uint32_t bh[NPW][2], bl[NPW][2];
 #pragma unroll
       for (int nt = 0; nt < NPW; ++nt) {
         const int n0 = (warp + nt * NWARP) * 8;
         if (n0 < ncols8) {
           const float* w0 = tile + (i0 + lr) * ldp + n0 + lq;
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(w0[0], bh0, bl0);
-          split_tf32(w0[4 * ldp], bh1, bl1);
+          split_tf32(w0[0], bh[nt][0], bl[nt][0]);
+          split_tf32(w0[4 * ldp], bh[nt][1], bl[nt][1]);
+        }
+      }
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            mma_3x(acc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
-            if (dual) mma_3x(acc2[mt][nt], a2h[mt], a2l[mt], bh0, bh1, bl0, bl1);
+      for (int term = 0; term < 3; ++term) {
+        if (term == 2 && a_exact && (!dual || a2_exact)) continue;   // no low parts (binary / integer inputs)
+#pragma unroll
+        for (int nt = 0; nt < NPW; ++nt) {
+          const int n0 = (warp + nt * NWARP) * 8;
+          if (n0 < ncols8) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (term == 0) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
+              else if (term == 1) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+              else if (!a_exact) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+              if (dual) {     // second input: round(v0) is integer-valued -> exact in tf32, no low term
+                if (term == 0) mma_tf32(acc2[mt][nt], a2h[mt], bh[nt][0], bh[nt][1]);
+                else if (term == 1) mma_tf32(acc2[mt][nt], a2h[mt], bl[nt][0], bl[nt][1]);
+                else if (!a2_exact) mma_tf32(acc2[mt][nt], a2l[mt], bh[nt][0], bh[nt][1]);
+              }
+            }
           }
         }
       }
@@ -340,19 +371,21 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   };
 
   auto load_hs = [&](const float* src, int ld_src, int nrows_src) {
+    int pred = 1;
     for (int e = tid; e < BT * ldw; e += NT) {
       int b = e / ldw, j = e % ldw;
       float x = 0.f;
       if (b < nrows_src && j < H) x = __ldcg(&src[(size_t)b * ld_src + j]);
       hs[b * ldh + j] = x;
+      pred &= ((__float_as_uint(x) & 0x1FFFu) == 0u) ? 1 : 0;
     }
-    __syncthreads();
+    return __syncthreads_and(pred) != 0;      // {0,1} chain states are exact in tf32
   };
 
   // =============================== pass 0: positive phase ===============================
   {
     const int depth = p.nslots;
-    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth);
+    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth, p.TR, p.slot_bytes);
     float acc[MT][NPW][4], acc2[MT][NPW][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -364,9 +397,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       wait_stage(st);
       const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
       const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7;
-      up_mma(tile, v0s + (size_t)j * p.TR * BTS, nvs + (size_t)j * p.TR * BTS, nr8, acc, acc2, ALLOW_DUAL && p.pcd != 0);
+      up_mma(tile, v0s + (size_t)j * p.TR * BTS, nvs + (size_t)j * p.TR * BTS, nr8, acc, acc2, ALLOW_DUAL && p.pcd != 0, v0_exact,
+             x_exact);
       __syncthreads();
-      if (warp == 0) issue(j + depth, 1, depth);
+      if (warp == 0) issue(j + depth, 1, depth, p.TR, p.slot_bytes);
     }
     mark();   // pass-0 tiles done
     flush_partial(acc, 0);
@@ -379,8 +413,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   reduce_hidden(p.pcd ? 2 : 1, p.PH, seg(0, 0), !p.pcd, false);
   mark();   // reduce 0 done
   grid_sync(p.bar, bar_target);
-  if (warp == 0) issue(0, 1, p.nslots);     // W is unchanged until the update: prefetch the next pass now
-  if (p.pcd) load_hs(p.P, H, B); else load_hs(p.HS, ldw, BT);
+  if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);     // W is unchanged until the update: prefetch the next pass now
+  bool h_exact = p.pcd ? load_hs(p.P, H, B) : load_hs(p.HS, ldw, BT);
   mark();
 
   // pseudo-likelihood monitor (src/rbm.py:421-447) — CTA 0, uses the pre-update W, hb, vb
@@ -422,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s);
     const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s);
     const int depth = p.nslots;
-    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth);   // job 0 was prefetched
+    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth, p.TR, p.slot_bytes);   // job 0 was prefetched
     float acc[MT][NPW][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -432,37 +466,56 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
 
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
+      if (j < 3) mark2();
       wait_stage(st);
+      if (j < 3) mark2();
       const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
       const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7, ntd = nr8 >> 3;
       // ---- propdown of the tile rows: out[b, i] = sum_j h[b][j] W[i][j]; the 8 warps split j ----
+      // mma.sync has a long dependent-issue latency on sm_100: every split term (and, for one
+      // m-tile, every other k-step) gets its own accumulator so ~3*KI*ntd MMAs are in flight
       {
-        float dacc[MT][NTD][4];
+        constexpr int KI = MT == 1 ? 2 : 1;
+        float dacc[KI][3][MT][NTD][4];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int ki = 0; ki < KI; ++ki)
 #pragma unroll
-          for (int nt = 0; nt < NTD; ++nt)
+          for (int t3 = 0; t3 < 3; ++t3)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dacc[mt][nt][c] = 0.f;
-        for (int j0 = warp * 8; j0 < ncols8; j0 += NWARP * 8) {
-          uint32_t ah[MT][4], al[MT][4];
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const float* h0 = hs + (mt * 16 + lq) * ldh + j0 + lr;
-            split_tf32(h0[0], ah[mt][0], al[mt][0]);
-            split_tf32(h0[8 * ldh], ah[mt][1], al[mt][1]);
-            split_tf32(h0[4], ah[mt][2], al[mt][2]);
-            split_tf32(h0[8 * ldh + 4], ah[mt][3], al[mt][3]);
-          }
+              for (int nt = 0; nt < NTD; ++nt)
 #pragma unroll
-          for (int nt = 0; nt < NTD; ++nt) {
-            if (nt < ntd) {
-              const float* w0 = tile + (nt * 8 + lq) * ldp + j0 + lr;
-              uint32_t bh0, bl0, bh1, bl1;
-              split_tf32(w0[0], bh0, bl0);
-              split_tf32(w0[4], bh1, bl1);
+                for (int c = 0; c < 4; ++c) dacc[ki][t3][mt][nt][c] = 0.f;
+        for (int jb = warp * 8; jb < ncols8; jb += NWARP * 8 * KI) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) mma_3x(dacc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+          for (int ki = 0; ki < KI; ++ki) {
+            const int j0 = jb + ki * NWARP * 8;
+            if (j0 < ncols8) {
+              uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const float* h0 = hs + (mt * 16 + lq) * ldh + j0 + lr;
+                split_tf32(h0[0], ah[mt][0], al[mt][0]);
+                split_tf32(h0[8 * ldh], ah[mt][1], al[mt][1]);
+                split_tf32(h0[4], ah[mt][2], al[mt][2]);
+                split_tf32(h0[8 * ldh + 4], ah[mt][3], al[mt][3]);
+              }
+#pragma unroll
+              for (int nt = 0; nt < NTD; ++nt) {
+                if (nt < ntd) {
+                  const float* w0 = tile + (nt * 8 + lq) * ldp + j0 + lr;
+                  uint32_t bh0, bl0, bh1, bl1;
+                  split_tf32(w0[0], bh0, bl0);
+                  split_tf32(w0[4], bh1, bl1);
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    mma_tf32(dacc[ki][0][mt][nt], ah[mt], bh0, bh1);
+                    mma_tf32(dacc[ki][1][mt][nt], ah[mt], bl0, bl1);
+                    if (!h_exact) mma_tf32(dacc[ki][2][mt][nt], al[mt], bh0, bh1);
+                  }
+                }
+              }
             }
           }
         }
@@ -471,14 +524,27 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
           if (nt < ntd) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
+              float r4[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float small = dacc[0][1][mt][nt][c] + dacc[0][2][mt][nt][c];
+                float big = dacc[0][0][mt][nt][c];
+                if (KI == 2) {
+                  small += dacc[KI - 1][1][mt][nt][c] + dacc[KI - 1][2][mt][nt][c];
+                  big += dacc[KI - 1][0][mt][nt][c];
+                }
+                r4[c] = big + small;
+              }
               float* d0 = dred + ((size_t)warp * MB + mt * 16 + lq) * p.TR + nt * 8 + 2 * lr;
-              *reinterpret_cast<float2*>(d0) = make_float2(dacc[mt][nt][0], dacc[mt][nt][1]);
-              *reinterpret_cast<float2*>(d0 + 8 * p.TR) = make_float2(dacc[mt][nt][2], dacc[mt][nt][3]);
+              *reinterpret_cast<float2*>(d0) = make_float2(r4[0], r4[1]);
+              *reinterpret_cast<float2*>(d0 + 8 * p.TR) = make_float2(r4[2], r4[3]);
             }
           }
         }
       }
+      if (j < 3) mark2();
       __syncthreads();
+      if (j < 3) mark2();
       // ---- visible epilogue: bias, activation, sampling (src/rbm.py:226-240 / :650-660) ----
       for (int it = tid; it < nr8 * MB; it += NT) {
         const int r = it / MB, b = it % MB;
@@ -506,10 +572,11 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         if (last) nvs[(j * p.TR + r) * BTS + b] = mean;
       }
       __syncthreads();
+      if (j < 3) mark2();
       // ---- propup accumulation from the same tile ----
-      up_mma(tile, vt, vt, nr8, acc, acc, false);
+      up_mma(tile, vt, vt, nr8, acc, acc, false, p.kind == MDBN_RBM, true);
       __syncthreads();
-      if (warp == 0) issue(j + depth, 1, depth);
+      if (warp == 0) issue(j + depth, 1, depth, p.TR, p.slot_bytes);
     }
     if (last) mark();   // Gibbs tiles done
     flush_partial(acc, 0);
@@ -523,16 +590,20 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     grid_sync(p.bar, bar_target);
     if (last) mark();
     if (!last) {
-      if (warp == 0) issue(0, 1, p.nslots);
-      load_hs(p.HS, ldw, BT);
+      if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);
+      h_exact = load_hs(p.HS, ldw, BT);
     }
   }
 
   // =============================== statistics + update ===============================
   {
+    // short tiles (8 rows) for this pass: it streams 2-3 arrays and wants a deep pipeline
     const int narr = p.wc != 0.f ? 3 : 2;
-    const int depth = p.nslots / narr;
-    if (warp == 0) for (int j = 0; j < depth; ++j) issue(j, narr, depth);
+    const int TRS = 8, slot_s = (TRS * ldp * 4 + 127) & ~127;
+    int depth = (p.nslots * p.slot_bytes) / (narr * slot_s);
+    depth = depth > MAX_SLOTS ? MAX_SLOTS : depth;
+    const int ntiles_s = (rows + TRS - 1) / TRS;
+    if (warp == 0) for (int j = 0; j < depth; ++j) issue(j, narr, depth, TRS, slot_s);
     const int ldw4 = ldw >> 2;
     float4 ph[BT], nh[BT];
 #pragma unroll
@@ -545,16 +616,16 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       }
     }
     const int ncol = min(4, H - 4 * q);
-    for (int j = 0, stg = 0; j < ntiles; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
+    for (int j = 0, stg = 0; j < ntiles_s; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
       wait_stage(stg);
-      const unsigned char* sb = smem + (size_t)stg * narr * p.slot_bytes;
+      const unsigned char* sb = smem + (size_t)stg * narr * slot_s;
       const float4* wt = reinterpret_cast<const float4*>(sb);
-      const float4* st = reinterpret_cast<const float4*>(sb + p.slot_bytes);
-      const float4* sn = reinterpret_cast<const float4*>(sb + 2 * (size_t)p.slot_bytes);
-      const int nr = min(p.TR, rows - j * p.TR);
+      const float4* st = reinterpret_cast<const float4*>(sb + slot_s);
+      const float4* sn = reinterpret_cast<const float4*>(sb + 2 * (size_t)slot_s);
+      const int nr = min(TRS, rows - j * TRS);
       if (col_ok) {
         for (int r = g; r < nr; r += p.G) {
-          const int lr_ = j * p.TR + r;
+          const int lr_ = j * TRS + r;
           float4 w = wt[r * ldp4 + q], sp = st[r * ldp4 + q];
           const float4* a4 = reinterpret_cast<const float4*>(v0s + lr_ * BTS);
           const float4* n4 = reinterpret_cast<const float4*>(nvs + lr_ * BTS);
@@ -603,7 +674,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         }
       }
       __syncthreads();
-      if (warp == 0) issue(j + depth, narr, depth);
+      if (warp == 0) issue(j + depth, narr, depth, TRS, slot_s);
     }
     // visible bias (rows owned by this CTA)  src/rbm.py:417
     for (int r = tid; r < rows; r += NT) {
@@ -680,7 +751,9 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
   g.rows_alloc = (g.rows_per_cta + 7) & ~7;
   g.n_active = (a.V + g.rows_per_cta - 1) / g.rows_per_cta;
-  g.ldp = pad_mod32(a.ldw > ncols8 ? a.ldw : ncols8, 24);
+  if (a.ldw != ncols8) return g;      // rows padded to 8 floats (the Python host allocates W that way)
+  g.ldp = a.ldw;                      // staged rows keep the global stride: one bulk copy per tile
+
   g.ldh = pad_mod32(ncols8, 20);
   int tr = (40 * 1024) / (g.ldp * 4);
   tr &= ~7;
@@ -790,7 +863,7 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.cost_part = p.PREX + hb_f;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
-  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;
+  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;   // needs 32 slots
   int rc = 2;
   if (g.BT == 10 && g.NPW == 8) rc = sk::launch<10, 8>(c, p, g, st);
   else if (g.BT == 10 && g.NPW == 16) rc = sk::launch<10, 16>(c, p, g, st);
@@ -798,11 +871,13 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   else if (g.BT == 20 && g.NPW == 16) rc = sk::launch<20, 16>(c, p, g, st);
   else set_error("skinny path: no kernel for BT=%d NPW=%d", g.BT, g.NPW);
   if (rc == 0 && p.dbg) {
-    unsigned long long t[16];
+    unsigned long long t[32];
     MDBN_CUDA(cudaStreamSynchronize(st));
     MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[skinny timeline us] V=%d H=%d B=%d k=%d:", a.V, a.H, a.B, a.k);
     for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
+    fprintf(stderr, "\n   gibbs tiles (wait< wait> D sync epi | ...):");
+    for (int i = 16; i < 31; ++i) fprintf(stderr, " %.2f", (double)(t[i] - t[0]) * 1e-3);
     fprintf(stderr, "\n");
   }
   return rc;

@@ -61,7 +61,7 @@ class DBN(object):
                 W = W_list[i]
             b = numpy.zeros((n_out,), dtype=numpy.float32) if b_list is None else b_list[i]
             sigmoid_layer = HiddenLayer(rng=numpy_rng, input=None, n_in=n_in, n_out=n_out,
-                                        W=Shared(W, name='W', device=self.device, ld_pad=4),
+                                        W=Shared(W, name='W', device=self.device, ld_pad=8),
                                         b=Shared(b, name='b', device=self.device), device=self.device)
             self.sigmoid_layers.append(sigmoid_layer)
             self.params.extend(sigmoid_layer.params)

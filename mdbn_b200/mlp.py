@@ -25,7 +25,7 @@ class HiddenLayer(object):
                 W_values *= 4                                            # src/mlp.py:90-91
             W = W_values
         if not isinstance(W, Shared):
-            W = Shared(W, name='W', device=self.device, ld_pad=4)
+            W = Shared(W, name='W', device=self.device, ld_pad=8)
         if b is None:
             b = numpy.zeros((n_out,), dtype=numpy.float32)
         if not isinstance(b, Shared):

@@ -18,7 +18,7 @@ from . import _lib
 from .rng import RandomStreams, BufferStreams, ExplicitBuffer
 from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx
 
-_PAD = 4   # W rows padded to 16 bytes so the streaming kernels can bulk-copy row slabs
+_PAD = 8   # W rows padded to 8 floats: 16-byte aligned bulk copies + whole 8-column MMA tiles
 
 
 def _ptr(t):
