@@ -49,6 +49,9 @@ int mdbn_create(mdbn_ctx** out, int device);
 int mdbn_destroy(mdbn_ctx* ctx);
 /* number of kernels this context has launched (diagnostic; bench.py's gpu_launches) */
 unsigned long long mdbn_launch_count(const mdbn_ctx* ctx);
+/* enable != 0: the single-phase calls below (propup / propdown) run on the tcgen05 TF32 tensor-core
+ * path (tolerance 2e-3) instead of the fp32 path, when their operands are 16-byte aligned */
+int mdbn_set_tf32_phases(mdbn_ctx* ctx, int enable);
 
 /* pre = v W + hbias ; mean = sigmoid(pre) ; sample = (u < mean).  Any of the three
  * outputs may be NULL (sample requires rng->mode != NONE).

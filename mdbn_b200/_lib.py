@@ -40,6 +40,7 @@ class CdArgs(C.Structure):
 
 
 EXPORTS = ("mdbn_abi_version", "mdbn_last_error", "mdbn_create", "mdbn_destroy", "mdbn_launch_count",
+           "mdbn_set_tf32_phases",
            "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_stats_size")
 
 _lib = None
@@ -65,6 +66,7 @@ def load():
         lib.mdbn_destroy.argtypes = [vp]
         lib.mdbn_launch_count.argtypes = [vp]
         lib.mdbn_launch_count.restype = C.c_ulonglong
+        lib.mdbn_set_tf32_phases.argtypes = [vp, i]
         lib.mdbn_stats_size.argtypes = [i, i]
         lib.mdbn_stats_size.restype = C.c_longlong
         lib.mdbn_propup.argtypes = [vp, vp, i, vp, vp, i, i, i, i, vp, vp, vp, C.POINTER(Rng), vp]
@@ -93,6 +95,10 @@ class Context:
         h = C.c_void_p()
         check(self.lib.mdbn_create(C.byref(h), self.device))
         self.handle = h
+
+    def set_tf32_phases(self, enable):
+        """Single-phase calls (propup/propdown/sample_*) on the tcgen05 TF32 path (tolerance 2e-3)."""
+        check(self.lib.mdbn_set_tf32_phases(self.handle, int(bool(enable))))
 
     @property
     def launches(self):

@@ -76,6 +76,12 @@ int mdbn_destroy(mdbn_ctx* c) {
 
 unsigned long long mdbn_launch_count(const mdbn_ctx* c) { return c ? c->launches : 0; }
 
+int mdbn_set_tf32_phases(mdbn_ctx* c, int enable) {
+  MDBN_CHECK(c != nullptr, "ctx is NULL");
+  c->tf32_phases = enable != 0;
+  return 0;
+}
+
 long long mdbn_stats_size(int V, int H) { return (long long)V * H + H + V + 2; }
 
 static int check_common(const mdbn_ctx* c, const void* W, int ldw, int B, int V, int H) {
@@ -94,6 +100,9 @@ int mdbn_propup(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const 
   MDBN_CHECK(!(rng && rng->mode == MDBN_RNG_BUFFER && sample_out) || rng->buffer, "propup: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
+  if (c->tf32_phases && tensor_phase_supported(W, ldw, v, ldv))
+    return tensor_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
+                         make_seg(rng ? *rng : none, 0, 0), (cudaStream_t)stream);
   return generic_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
                         make_seg(rng ? *rng : none, 0, 0), (cudaStream_t)stream);
 }
@@ -109,6 +118,9 @@ int mdbn_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vbias, cons
   MDBN_CHECK(!(needs_rng && rng->mode == MDBN_RNG_BUFFER) || rng->buffer, "propdown: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
+  if (c->tf32_phases && tensor_phase_supported(W, ldw, h, ldh))
+    return tensor_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
+                           make_seg(rng ? *rng : none, 0, 1), (cudaStream_t)stream);
   return generic_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
                           make_seg(rng ? *rng : none, 0, 1), (cudaStream_t)stream);
 }

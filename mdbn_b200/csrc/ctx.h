@@ -15,6 +15,7 @@ struct mdbn_ctx {
   struct Buf { void* p = nullptr; size_t n = 0; };
   Buf ws[16];
   unsigned int* barrier = nullptr;   // grid barrier word for the persistent kernel
+  int tf32_phases = 0;               // single-phase calls use the tcgen05 TF32 path (mdbn_set_tf32_phases)
 };
 
 namespace mdbn {
@@ -79,6 +80,12 @@ int skinny_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
 // ---- tcgen05 / TMA path (large batch, TF32): tensor.cu ----------------------
 bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int tensor_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
+bool tensor_phase_supported(const void* W, int ldw, const void* x, long long ldx);
+int tensor_propup(mdbn_ctx*, const float* W, int ldw, const float* hb, const float* v, int ldv, int B, int V, int H,
+                  float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
+int tensor_propdown(mdbn_ctx*, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
+                    int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
+int apply_update(mdbn_ctx* c, const mdbn_cd_args& a, const float* G, int rows, cudaStream_t st);
 
 // layout of the App. A random buffer
 struct ULayout {

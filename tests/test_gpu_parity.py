@@ -322,3 +322,94 @@ def test_size_independent_properties_full_size():
     assert outs[0][0] == outs[1][0]
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][1]).max() > 0
+
+
+# ---------------------------------------------------------------------------
+# tcgen05 / TMA large-batch path (TF32, tolerance 2e-3 relative)
+# ---------------------------------------------------------------------------
+TF32_RTOL = 2e-3
+
+
+@pytest.mark.parametrize("shape", [(128, 784, 500), (64, 200, 72), (70, 132, 52), (256, 1000, 1000), (32, 100, 24)],
+                         ids=lambda s: "B%d_V%d_H%d" % s)
+@pytest.mark.parametrize("kind", [O.RBM, O.GRBM])
+def test_tensor_phases_vs_oracle(shape, kind):
+    B, V, H = shape
+    m = M()
+    rs = np.random.RandomState(B + V)
+    L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(7), dtype=np.float64)
+    L.W[...] = L.W.astype(np.float32)
+    L.hbias[...] = (rs.randn(H) * 0.2).astype(np.float32)
+    L.vbias[...] = (rs.randn(V) * 0.2).astype(np.float32)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    r = cls(n_visible=V, n_hidden=H, W=L.W.astype(np.float32))
+    r.hbias.set_value(L.hbias)
+    r.vbias.set_value(L.vbias)
+    v = synth(kind, B, V, seed=3).astype(np.float64)
+    h = (rs.rand(B, H) < 0.5).astype(np.float64)
+    uh = ((rs.randint(0, 1 << 24, (B, H)) + 0.5) / (1 << 24)).astype(np.float32)
+    uv = ((rs.randint(0, 1 << 24, (B, V)) + 0.5) / (1 << 24)).astype(np.float32)
+    r.ctx.set_tf32_phases(True)
+    try:
+        n0 = r.ctx.launches
+        pre, mean, smp = r.sample_h_given_v(v.astype(np.float32), u=uh)
+        pre_o, mean_o, _ = O.sample_h_given_v(L, v, uh.astype(np.float64))
+        # error model of TF32: each product carries 2^-11 relative error -> scale by sum |x||W|
+        scale = (np.abs(v) @ np.abs(L.W)).max()
+        close(pre, pre_o, rtol=TF32_RTOL, scale=scale, what="tf32 propup pre")
+        close(mean, mean_o, rtol=TF32_RTOL, scale=1.0, what="tf32 propup mean")
+        s = smp.cpu().numpy()
+        bad = s != (uh < mean_o)
+        assert (np.abs(uh - mean_o)[bad] < TF32_RTOL).all(), "hidden sample flips away from a tie"
+        out = r.sample_v_given_h(h.astype(np.float32), u=uv)
+        pv_o, mv_o, _ = O.sample_v_given_h(L, h, uv.astype(np.float64))
+        scale = (np.abs(h) @ np.abs(L.W.T)).max()
+        close(out[0], pv_o, rtol=TF32_RTOL, scale=scale, what="tf32 propdown pre")
+        close(out[1], mv_o, rtol=TF32_RTOL, scale=max(1.0, np.abs(mv_o).max()), what="tf32 propdown mean")
+        if kind == O.RBM:
+            s = out[2].cpu().numpy()
+            bad = s != (uv < mv_o)
+            assert (np.abs(uv - mv_o)[bad] < TF32_RTOL).all(), "visible sample flips away from a tie"
+        assert r.ctx.launches - n0 == 2, "expected exactly one fused tcgen05 kernel per phase"
+    finally:
+        r.ctx.set_tf32_phases(False)
+
+
+TENSOR_STEPS = [
+    ("rbm_784x500_b128_cd1", O.RBM, 784, 500, 128, 1, False, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("rbm_784x500_b256_pcd2", O.RBM, 784, 500, 256, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("grbm_1000x64_b64_cd1", O.GRBM, 1000, 64, 64, 1, False, 0.005, 0.0, 0.01, 0.1, 0.0),
+    ("grbm_2000x400_b96_pcd1", O.GRBM, 2000, 400, 96, 1, True, 0.005, 0.0, 0.01, 0.1, 0.0),
+]
+
+
+@pytest.mark.parametrize("cfg", TENSOR_STEPS, ids=[c[0] for c in TENSOR_STEPS])
+def test_tensor_cd_step_tracks_oracle(cfg):
+    """Whole step on the tensor path.  TF32 pre-activations move a ~1e-3 fraction of the Bernoulli
+    draws across their thresholds, so the step is compared as a whole with the statistical bars:
+    cost within 1 %, gradient (= the speeds after one step) within 1 % in Frobenius norm."""
+    name, kind, V, H, B, k, pcd, lr, mom, l1, l2, wc = cfg
+    m = M()
+    data = synth(kind, B, V, seed=11)
+    L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(123), dtype=np.float64)
+    L.W[...] = L.W.astype(np.float32)
+    W0 = L.W.copy()
+    prov = lambda layer, call, b: shared_u.step_buffer(77, layer, call, kind, True, b, V, H, k)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    r = cls(n_visible=V, n_hidden=H, W=W0.astype(np.float32), theano_rng=m.BufferStreams(prov))
+    P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+    Po = np.zeros((B, H)) if pcd else None
+    cost, upd = r.get_cost_updates(lr=lr, k=k, lambda_1=l1, lambda_2=l2, weightcost=wc, batch_size=B, persistent=P)
+    fn = r.make_train_fn(data, cost, upd, path="tensor", tf32=True)
+    idx = np.arange(B, dtype=np.int32)
+    c = fn(idx, mom)
+    co = O.cd_step(L, data.astype(np.float64), prov(0, 0, B), lr=lr, k=k, lambda_1=l1, lambda_2=l2, weightcost=wc,
+                   batch_size=B, momentum=mom, persistent=Po, W_snap=W0)
+    assert abs(c - co) <= 1e-2 * abs(co), (c, co)
+    for a, b, nm in ((r.W_speed.get_value(), L.W_speed, "W_speed"), (r.hbias_speed.get_value(), L.hbias_speed, "hb_speed"),
+                     (r.vbias_speed.get_value(), L.vbias_speed, "vb_speed")):
+        rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert rel < 1e-2, "%s relative error %.3e" % (nm, rel)
+    close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W (first step moves W by mult only)")
+    if Po is not None:
+        assert (P.get_value() != Po).mean() < 0.02
