@@ -69,14 +69,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// shared-memory matrix descriptor (SM100 UMMA), 128-byte swizzle
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (SM100 UMMA).  K-major tiles use the plain 128-byte swizzle (16-byte
+// chunks); MN-major TF32 operands only exist in the 128-byte swizzle with 32-byte atoms (4-row period).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);             // [0,14)  start address >> 4
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // [16,30) leading byte offset >> 4
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // [32,46) stride byte offset >> 4
   d |= (uint64_t)1 << 46;                               // [46,48) descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                               // [61,64) SWIZZLE_128B
+  d |= (uint64_t)layout << 61;                          // [61,64) 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
 #pragma unroll
       for (int kk = 0; kk < BK / 8; ++kk) {
         // K-major: 8 floats = 32 bytes along the swizzled row; MN-major: 8 K-rows = 1024 bytes
-        const uint64_t ad = A_MN ? make_desc(sa + kk * 1024, BK * 128, 1024) : make_desc(sa + kk * 32, 16, 1024);
-        const uint64_t bd = B_MN ? make_desc(sb + kk * 1024, BK * 128, 1024) : make_desc(sb + kk * 32, 16, 1024);
+        const uint64_t ad = A_MN ? make_desc(sa + kk * 1024, BK * 128, 512, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
+        const uint64_t bd = B_MN ? make_desc(sb + kk * 1024, BK * 128, 512, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
         umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
       }
       umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs have read it
@@ -250,7 +251,7 @@ static EncodeFn get_encode() {
 
 // operand matrix in memory: [outer][inner] row-major with row stride ld (floats)
 static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long ld, int box_inner,
-                    int box_outer) {
+                    int box_outer, bool mn_major) {
   EncodeFn enc = get_encode();
   MDBN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   MDBN_CHECK(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, "TMA operand must be 16-byte aligned (ptr %p ld %lld)",
@@ -260,7 +261,9 @@ static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long lon
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MDBN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;
@@ -276,8 +279,8 @@ template <bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(mdbn_ctx* c, const Operand& A, const Operand& Bo, int M, int N, int K, int splits, int kneg,
                        const EpiParams& ep, cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  if (A_MN) MDBN_TRY(make_map(&tmA, A.ptr, M, K, A.ld, 32, BK)); else MDBN_TRY(make_map(&tmA, A.ptr, K, M, A.ld, BK, BM));
-  if (B_MN) MDBN_TRY(make_map(&tmB, Bo.ptr, N, K, Bo.ld, 32, BK)); else MDBN_TRY(make_map(&tmB, Bo.ptr, K, N, Bo.ld, BK, BN));
+  if (A_MN) MDBN_TRY(make_map(&tmA, A.ptr, M, K, A.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmA, A.ptr, K, M, A.ld, BK, BM, false));
+  if (B_MN) MDBN_TRY(make_map(&tmB, Bo.ptr, N, K, Bo.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmB, Bo.ptr, K, N, Bo.ld, BK, BN, false));
   auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
   static bool configured[64] = {};
   if (!configured[c->device]) {

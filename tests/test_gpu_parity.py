@@ -408,7 +408,8 @@ def test_tensor_cd_step_tracks_oracle(cfg):
     assert abs(c - co) <= 1e-2 * abs(co), (c, co)
     for a, b, nm in ((r.W_speed.get_value(), L.W_speed, "W_speed"), (r.hbias_speed.get_value(), L.hbias_speed, "hb_speed"),
                      (r.vbias_speed.get_value(), L.vbias_speed, "vb_speed")):
-        rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+        # floor: z-scored minibatches have exactly-zero column means, so a speed can be pure round-off
+        rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-3 * np.sqrt(b.size))
         assert rel < 1e-2, "%s relative error %.3e" % (nm, rel)
     close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W (first step moves W by mult only)")
     if Po is not None:
