@@ -67,6 +67,8 @@ class TrainFn:
         self._keep = None
         self.n_calls = 0
         self.sync = True            # return a Python float (like the reference); False -> device scalar
+        self.dp = None              # parallel.DataParallel: shard the minibatch rows + all-reduce the statistics
+        self._stats = None
 
     def data(self):
         """Device-resident input matrix of this layer.  For a stacked layer it is the
@@ -80,20 +82,46 @@ class TrainFn:
         return self._data
 
     def __call__(self, indexes=None, momentum=0.0, lr=None, rows=None):
+        if self.dp is not None and self.dp.world > 1:
+            return self._call_dp(indexes, momentum, lr)
+        return self._call(indexes, momentum, lr)
+
+    def _call_dp(self, indexes, momentum, lr):
+        """Large-batch CD split over ranks: STATS on this rank's rows -> all-reduce -> APPLY."""
+        from .parallel import stats_size
+        r = self.rbm
+        if self._stats is None:
+            self._stats = torch.zeros(stats_size(r.n_visible, r.n_hidden), dtype=torch.float32, device=self.device)
+        n_total = len(indexes)
+
+        def stats_fn(mine):
+            self._call(mine, momentum, lr, phase=_lib.PHASE_STATS)
+            return self._stats
+
+        def apply_fn(buf, rows_total):
+            return self._call(None, momentum, lr, phase=_lib.PHASE_APPLY, rows_total=rows_total)
+        return self.dp.step(indexes, stats_fn, apply_fn)
+
+    def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0):
         r, h = self.rbm, self.updates.hyper
         data = self.data()
-        if isinstance(indexes, torch.Tensor):
+        if indexes is None:                      # APPLY phase: no rows of its own
+            idx = torch.zeros(1, dtype=torch.int32, device=self.device)
+        elif isinstance(indexes, torch.Tensor):
             idx = indexes.to(device=self.device, dtype=torch.int32)
         else:
             idx = torch.as_tensor(numpy.asarray(indexes, dtype=numpy.int32)).to(self.device)
         B = int(idx.numel())
         persistent = h.get("persistent")
-        if persistent is not None and persistent.shape[0] != B:
+        if persistent is not None and persistent.shape[0] != B and phase != _lib.PHASE_APPLY:
             raise ValueError("PCD chain has %d rows but the minibatch has %d (the reference fails the same way)"
                              % (persistent.shape[0], B))
         if h["batch_size"] is None:
             raise TypeError("batch_size=None: the W statistics are divided by batch_size (src/rbm.py:413)")
-        rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B)
+        if phase == _lib.PHASE_APPLY:
+            rng, keep = _lib.Rng(_lib.RNG_PHILOX, None, 0, 0), None
+        else:
+            rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B)
         a = _lib.CdArgs()
         a.kind, a.noisy = r.kind, int(not getattr(r, "error_free", True))
         a.B, a.B_nom, a.V, a.H, a.k = B, int(h["batch_size"]), r.n_visible, r.n_hidden, int(h["k"])
@@ -111,10 +139,16 @@ class TrainFn:
         a.lambda_1, a.lambda_2, a.weightcost = float(h["lambda_1"]), float(h["lambda_2"]), float(h["weightcost"])
         a.rng = rng
         a.cost_out = self.cost_dev.data_ptr()
-        a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), _lib.PHASE_FULL
+        a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), phase
+        if phase != _lib.PHASE_FULL:
+            a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
+            if a.path == _lib.PATH_SKINNY:
+                a.path = _lib.PATH_AUTO
         _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
         self._keep = (keep, idx, data)
         self.n_calls += 1
+        if phase == _lib.PHASE_STATS:
+            return None
         for s in (r.W, r.hbias, r.vbias):
             s.version += 1
         if not self.sync:

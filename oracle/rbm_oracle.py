@@ -258,6 +258,60 @@ def cd_step(L, v0, U, lr=0.1, k=1, lambda_1=0.0, lambda_2=0.0, weightcost=0.0,
 
 
 # ---------------------------------------------------------------------------
+# the same step split at the data-parallel cut (SURVEY.md 8e-2): raw row sums -> packed buffer ->
+# update.  cd_apply(cd_stats(...)) == cd_step(...) up to summation order.
+# ---------------------------------------------------------------------------
+def cd_stats(L, v0, U, k=1, persistent=None):
+    """[v0^T ph - nv^T nh (V*H) | sum(ph-nh) (H) | sum(v0-nv) (V) | cost numerator | rows] for these rows;
+    updates `persistent` (rows of the chain owned by the caller) but not the parameters."""
+    dt = L.W.dtype
+    B, V, H = v0.shape[0], L.n_visible, L.n_hidden
+    u = _views(np.asarray(U), L.kind, L.error_free, B, V, H, k)
+    f = lambda x: np.asarray(x, dtype=dt)
+    pre_h0, ph_mean, ph_sample = sample_h_given_v(L, v0, f(u["hpos"]))
+    h = ph_sample if persistent is None else persistent
+    for s in range(k):
+        uv = f(u["v%d" % s]) if ("v%d" % s) in u else None
+        pre_v, nv_mean, nv_sample, pre_h, nh_mean, h = gibbs_hvh(L, h, uv, f(u["h%d" % s]))
+    if persistent is not None:
+        xi = round_half_away(v0)
+        fe = free_energy(L, xi)
+        xf = xi.copy()
+        xf[:, L.bit_i_idx] = 1 - xi[:, L.bit_i_idx]
+        num = -np.sum(V * softplus(fe - free_energy(L, xf)))
+        persistent[...] = h
+    elif L.kind == GRBM:
+        num = np.square(sigmoid(pre_v) - v0).sum()
+    else:
+        num = (v0 * softplus(-pre_v) + (1.0 - v0) * softplus(pre_v)).sum()
+    return np.concatenate([(v0.T @ ph_mean - nv_mean.T @ nh_mean).ravel(), (ph_mean - nh_mean).sum(0),
+                           (v0 - nv_mean).sum(0), [num, B]]).astype(dt)
+
+
+def cd_apply(L, packed, lr, lambda_1=0.0, lambda_2=0.0, weightcost=0.0, batch_size=None, momentum=0.0,
+             W_snap=None, pcd=False):
+    dt = L.W.dtype
+    V, H = L.n_visible, L.n_hidden
+    rows = float(packed[-1])
+    lr, momentum, lambda_1, lambda_2, weightcost = map(dt.type, (lr, momentum, lambda_1, lambda_2, weightcost))
+    gW = packed[:V * H].reshape(V, H) / dt.type(batch_size) - (weightcost * W_snap if weightcost != 0 else 0)
+    ghb = packed[V * H:V * H + H] / dt.type(rows)
+    gvb = packed[V * H + H:V * H + H + V] / dt.type(rows)
+    D = 1 + 2 * lr * lambda_1 / (np.abs(L.W) + dt.type(EPSILON))
+    gW = gW / D
+    mult_W = (1 - 2 * lr * lambda_2) / D
+    den = rows * V if (not pcd and L.kind == GRBM) else rows
+    cost = packed[-2] / den
+    new = (L.W * mult_W + L.W_speed * lr, L.hbias + L.hbias_speed * lr, L.vbias + L.vbias_speed * lr,
+           gW + (L.W_speed - gW) * momentum, ghb + (L.hbias_speed - ghb) * momentum,
+           gvb + (L.vbias_speed - gvb) * momentum)
+    L.W[...], L.hbias[...], L.vbias[...], L.W_speed[...], L.hbias_speed[...], L.vbias_speed[...] = new
+    if pcd:
+        L.bit_i_idx = (L.bit_i_idx + 1) % V
+    return dt.type(cost)
+
+
+# ---------------------------------------------------------------------------
 # batching                               src/utils.py:54-75
 # ---------------------------------------------------------------------------
 def get_minibatches_idx(n, batch_size, shuffle=False, rng=None):

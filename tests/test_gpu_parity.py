@@ -414,3 +414,52 @@ def test_tensor_cd_step_tracks_oracle(cfg):
     close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W (first step moves W by mult only)")
     if Po is not None:
         assert (P.get_value() != Po).mean() < 0.02
+
+
+# ---------------------------------------------------------------------------
+# data-parallel contract at the C ABI: STATS over two half minibatches, summed, then APPLY
+# == one FULL step on the whole minibatch (linearity of the statistics, src/rbm.py:411-417)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path,tf32,B", [("generic", False, 20), ("generic", False, 64), ("tensor", True, 64)])
+@pytest.mark.parametrize("kind", [O.RBM, O.GRBM])
+def test_stats_apply_phases_equal_full_step(kind, path, tf32, B):
+    import ctypes
+    from mdbn_b200 import _lib
+    from mdbn_b200.parallel import stats_size
+    m = M()
+    V, H, k = 200, 72, 1
+    data = synth(kind, B, V, seed=21)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(4), V, H).astype(np.float32)
+    half = B // 2
+
+    def make(prov):
+        r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.BufferStreams(prov))
+        cost, upd = r.get_cost_updates(lr=0.05, k=k, lambda_1=0.01, lambda_2=0.1, weightcost=0.0002, batch_size=B)
+        fn = r.make_train_fn(data, cost, upd, path=path, tf32=tf32)
+        return r, fn
+    U = shared_u.step_buffer(8, 0, 0, kind, True, B, V, H, k)
+    lay, _ = O.u_layout(kind, True, B, V, H, k)
+
+    def rows_of(U, lo, hi):
+        return np.concatenate([U[o:o + sh[0] * sh[1]].reshape(sh)[lo:hi].ravel() for _, o, sh in lay])
+    # whole minibatch, one FULL step
+    r_full, fn_full = make(lambda layer, call, b: U)
+    c_full = fn_full(np.arange(B, dtype=np.int32), 0.5)
+    # two "ranks" on one GPU: each its own rows and its own slice of the random buffer
+    bufs = {}
+    r_dp, fn_dp = make(lambda layer, call, b: bufs["u"])
+    fn_dp._stats = torch.zeros(stats_size(V, H), dtype=torch.float32, device=r_dp.device)
+    total = torch.zeros_like(fn_dp._stats)
+    for lo, hi in ((0, half), (half, B)):
+        bufs["u"] = rows_of(U, lo, hi)
+        fn_dp._call(np.arange(lo, hi, dtype=np.int32), 0.5, None, phase=_lib.PHASE_STATS)
+        total += fn_dp._stats
+    assert float(total[-1]) == B
+    fn_dp._stats.copy_(total)
+    c_dp = fn_dp._call(None, 0.5, None, phase=_lib.PHASE_APPLY, rows_total=B)
+    tol = 2e-3 if tf32 else 2e-5
+    assert abs(c_dp - c_full) <= tol * abs(c_full) + 1e-6
+    for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        a, b = getattr(r_dp, name).get_value(), getattr(r_full, name).get_value()
+        close(a, b, rtol=tol, scale=max(np.abs(b).max(), 1e-4), what=name)
