@@ -39,6 +39,16 @@ WORKLOADS = {
                               l2=0.0, wc=0.0002),
     "mnist_rbm_pcd1_b20": dict(kind=0, V=784, H=500, B=20, k=1, pcd=True, N=49940, lr=0.1, mom=0.9, l1=0.0,
                                l2=0.0, wc=0.0002),
+    # BASELINE.json configs[4]: large-batch / many-chain PCD on the tcgen05 TF32 path; with --gpus N the
+    # minibatch rows (and chains) are sharded over ranks and the packed statistics all-reduced (strong scaling)
+    "rbm_784x500_b8192_pcd1_tf32": dict(kind=0, V=784, H=500, B=8192, k=1, pcd=True, N=65536, lr=0.1, mom=0.9,
+                                        l1=0.0, l2=0.0, wc=0.0002, tensor=True, dp=True),
+    "rbm_784x500_b1024_pcd1_tf32": dict(kind=0, V=784, H=500, B=1024, k=1, pcd=True, N=65536, lr=0.1, mom=0.9,
+                                        l1=0.0, l2=0.0, wc=0.0002, tensor=True, dp=True),
+    "rbm_784x500_b8192_pcd10_tf32": dict(kind=0, V=784, H=500, B=8192, k=10, pcd=True, N=65536, lr=0.1, mom=0.9,
+                                         l1=0.0, l2=0.0, wc=0.0002, tensor=True, dp=True),
+    "grbm_19937x400_b2048_cd1_tf32": dict(kind=1, V=19937, H=400, B=2048, k=1, pcd=False, N=4096, lr=0.005, mom=0.0,
+                                          l1=0.01, l2=0.1, wc=0.0, tensor=True, dp=True),
 }
 DEFAULT = "ge_grbm_pcd1_b10"
 
@@ -62,6 +72,32 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def algorithmic_flops(w):
+    """2 B V H (2k+3) flops per CD-k step (monitor GEMMs excluded)."""
+    return 2.0 * w["B"] * w["V"] * w["H"] * (2 * w["k"] + 3)
+
+
+def tf32_peak_tflops(torch, dev):
+    """TF32 is not in MEASURED_PEAKS.json: measured the way that file measures bf16 — cuBLAS
+    torch.matmul 8192^3 with TF32 enabled, best of 10 (burst)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    best = 1e9
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
 
 
 class ClockSampler:
@@ -192,19 +228,27 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     kind, V, H, B, k = w["kind"], w["V"], w["H"], w["B"], w["k"]
-    data_h = synth(kind, min(w["N"], 4096), V, 1 + rank)
+    tensor, dp = bool(w.get("tensor")), bool(w.get("dp")) and world > 1
+    path = "tensor" if tensor else "auto"
+    if dp:
+        assert B % world == 0
+    data_h = synth(kind, min(w["N"], 4096 if not tensor else 65536), V, 1 + (0 if dp else rank))
     data = torch.from_numpy(data_h).to(dev)
     cls = M.GRBM if kind == 1 else M.RBM
-    R = max(1, args.replicas)
+    R = max(1, args.replicas) if not tensor else 1     # large-batch working sets already exceed L2
+    Bl = B // world if dp else B                       # rows (and chains) this rank owns
     fns, layers = [], []
     for r in range(R):
         m = cls(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(123 + r),
                 theano_rng=M.RandomStreams(1000 + 17 * r + rank))
-        P = M.shared(np.zeros((B, H), np.float32)) if w["pcd"] else None
+        P = M.shared(np.zeros((Bl, H), np.float32)) if w["pcd"] else None
         cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
                                        batch_size=B, persistent=P)
-        fn = m.make_train_fn(data, cost, upd)
+        fn = m.make_train_fn(data, cost, upd, path=path, tf32=tensor)
         fn.sync = False
+        if dp:
+            from mdbn_b200.parallel import DataParallel
+            fn.dp = DataParallel()
         fns.append(fn)
         layers.append(m)
     ctx = layers[0].ctx
@@ -247,18 +291,22 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_warm = timed(args.steps, False)                         # same step, single parameter set (L2-warm)
     ms_per_step = ms / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    value = (1 if dp else world) * B / (ms_per_step * 1e-3)
 
     # ---- end to end: host minibatch -> pinned -> H2D -> step -> D2H cost, every step ----
-    host_mb = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, B)])).pin_memory() for _ in range(8)]
+    n_host = 8 if not tensor else 2
+    host_mb = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, B)])).pin_memory() for _ in range(n_host)]
     stage = torch.empty((B, V), dtype=torch.float32, device=dev)
     e2e_fns = []
     for r in range(R):
         m = layers[r]
-        P = M.shared(np.zeros((B, H), np.float32)) if w["pcd"] else None
+        P = M.shared(np.zeros((Bl, H), np.float32)) if w["pcd"] else None
         cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
                                        batch_size=B, persistent=P)
-        e2e_fns.append(m.make_train_fn(stage, cost, upd))       # sync=True: returns the cost as a Python float
+        f2 = m.make_train_fn(stage, cost, upd, path=path, tf32=tensor)   # sync=True: returns the cost as a Python float
+        if dp:
+            f2.dp = fns[0].dp
+        e2e_fns.append(f2)
     rows = torch.arange(B, dtype=torch.int32, device=dev)
     n_e2e = min(args.steps, 400)
 
@@ -278,7 +326,7 @@ def main():
         t = torch.tensor([t_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    e2e_value = world * B * n_e2e / t_e2e
+    e2e_value = (1 if dp else world) * B * n_e2e / t_e2e
 
     if rank == 0:
         peak, how = peaks()
@@ -288,23 +336,37 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload)
+        if tensor:
+            tpeak = tf32_peak_tflops(torch, dev)
+            aflops = algorithmic_flops(w) / (world if dp else 1)
+            ach = aflops / (ms_per_step * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": None, "kernel": "tc_gemm_kernel (tcgen05 tf32; %d GEMM launches per step)" % (2 * k + 2 + (1 if w["pcd"] else 0)),
+                    "peak_source": "measured here: torch.matmul 8192^3 TF32, best of 10 (MEASURED_PEAKS.json has no TF32 row)",
+                    "algorithmic_flops_per_step_per_gpu": aflops}
+        else:
+            roof = None
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if dp else "weak",
+            "vs_baseline": None, "dtype": "tf32" if tensor else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "layer": "%s %d->%d" % ("GRBM" if kind else "RBM", V, H),
                        "batch": B, "k": k, "pcd": w["pcd"], "rng": "philox4x32-10 in-kernel",
-                       "l2": "steps rotate over %d independent parameter sets (%.0f MB > L2) so weights stream from HBM"
-                             % (R, R * 2 * V * H * 4 / 1e6),
-                       "parallelism": "one independent layer per GPU (modality-parallel), no collective"},
+                       "l2": ("inputs larger than L2: activations + dataset of a %d-row batch" % B) if tensor else
+                             ("steps rotate over %d independent parameter sets (%.0f MB > L2) so weights stream from HBM"
+                              % (R, R * 2 * V * H * 4 / 1e6)),
+                       "parallelism": ("minibatch rows sharded over %d ranks + NCCL all-reduce of the packed statistics" % world)
+                       if dp else "one independent layer per GPU (modality-parallel), no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": 4,
                     "steps": n_e2e, "path": "RBM.make_train_fn -> mdbn_cd_step (C ABI), host minibatch from pinned memory"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "cd_skinny_kernel", "peak_source": how,
-                         "algorithmic_bytes_per_launch": abytes,
-                         "achieved_l2_warm": abytes / (ms_warm / args.steps * 1e-3) / 1e9},
+            "roofline": roof if roof else
+            {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+             "traffic": traffic, "kernel": "cd_skinny_kernel", "peak_source": how,
+             "algorithmic_bytes_per_launch": abytes,
+             "achieved_l2_warm": abytes / (ms_warm / args.steps * 1e-3) / 1e9},
             "value_l2_warm": world * B / (ms_warm / args.steps * 1e-3),
         }
         if not args.no_cpu_baseline:

@@ -142,8 +142,8 @@ class TrainFn:
         a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), phase
         if phase != _lib.PHASE_FULL:
             a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
-            if a.path == _lib.PATH_SKINNY:
-                a.path = _lib.PATH_AUTO
+            if a.path == _lib.PATH_SKINNY or phase == _lib.PHASE_APPLY:
+                a.path = _lib.PATH_AUTO      # the update from reduced statistics is one elementwise kernel
         _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
         self._keep = (keep, idx, data)
         self.n_calls += 1
