@@ -309,12 +309,32 @@ __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long 
     if (xi) xi[b * ldo + i] = roundf(x);
   }
 }
-__global__ void col_diff_sum_ld_kernel(const float* __restrict__ X, long long ld, int B, int N, float* __restrict__ out) {
+// raw column sums of (top half - bottom half) of a [2B, N] matrix, two deterministic stages:
+// row chunks in parallel, then a fixed-order sum of the chunk partials
+__global__ void col_diff_partial_kernel(const float* __restrict__ X, long long ld, int B, int N, int rows_per_chunk,
+                                        float* __restrict__ partial) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
   float p = 0.f, q = 0.f;
-  for (int b = 0; b < B; ++b) { p += X[(size_t)b * ld + n]; q += X[(size_t)(B + b) * ld + n]; }
-  out[n] = p - q;
+  for (int b = b0; b < b1; ++b) { p += X[(size_t)b * ld + n]; q += X[(size_t)(B + b) * ld + n]; }
+  partial[(size_t)blockIdx.y * N + n] = p - q;
+}
+__global__ void col_diff_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * N + n];
+  out[n] = s;
+}
+static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int N, float* out, cudaStream_t st) {
+  const int rpc = 32, chunks = (B + rpc - 1) / rpc;
+  float* part = (float*)ws_get(c, WS_MISC, (size_t)chunks * N * sizeof(float));
+  if (!part) return 3;
+  col_diff_partial_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, st>>>(X, ld, B, N, rpc, part);
+  col_diff_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, chunks, N, out);
+  c->launches += 2;
+  return 0;
 }
 __global__ void recon_cost_ld_kernel(const float* __restrict__ prev, const float* __restrict__ v0, long long ld, int B,
                                      int V, int kind, float* __restrict__ partial) {
@@ -483,10 +503,8 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, VH, G);
     c->launches++;
   }
-  col_diff_sum_ld_kernel<<<(H + 255) / 256, 256, 0, st>>>(YH, ldy, B, H, G + VH);
-  c->launches++;
-  col_diff_sum_ld_kernel<<<(V + 255) / 256, 256, 0, st>>>(XV, ldx, B, V, G + VH + H);
-  c->launches++;
+  MDBN_TRY(col_diff_sum(c, YH, ldy, B, H, G + VH, st));
+  MDBN_TRY(col_diff_sum(c, XV, ldx, B, V, G + VH + H, st));
   if (pcd) {
     pl_row_ld_kernel<<<B, 128, 0, st>>>(PREX, ldy, H, XI, ldx, V, a.W, a.ldw, a.vbias, a.bit_i_idx, a.kind, RED);
     c->launches++;
