@@ -41,6 +41,7 @@ struct EpiParams {
   float *pre, *mean, *sample;
   long long ld_pre, ld_mean, ld_sample;
   float* part;          // EPI_PART: [splits][M][N]
+  int vec4;             // all epilogue pointers 16-byte aligned, strides and N multiples of 4
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,6 +202,39 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+        } else if (ep.vec4 && nb + 32 <= N) {
+          // 4 columns per step: one Philox block feeds 4 draws, 16-byte stores
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nb + j;
+            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n);
+            float pre[4] = {__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                            __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w};
+            float mu[4], x[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) mu[t] = ep.act == ACT_SIGMOID ? sigmoidf_(pre[t]) : pre[t];
+            if (ep.pre) *reinterpret_cast<float4*>(ep.pre + m * ep.ld_pre + n) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+            if (ep.mean) *reinterpret_cast<float4*>(ep.mean + m * ep.ld_mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+            if (ep.sample) {
+              const long long e = (long long)m * N + n;      // multiple of 4 on this path
+              if (ep.smp == SMP_BERNOULLI) {
+                float u[4];
+                if (ep.rs.mode == MDBN_RNG_BUFFER) {
+                  const float4 uv = __ldg(reinterpret_cast<const float4*>(ep.rs.seg + e));
+                  u[0] = uv.x; u[1] = uv.y; u[2] = uv.z; u[3] = uv.w;
+                } else {
+                  Philox4 ph = philox4x32_10((uint32_t)(e >> 2), ep.rs.c1, ep.rs.c2, ep.rs.c3, ep.rs.k0, ep.rs.k1);
+                  u[0] = u24(ph.x); u[1] = u24(ph.y); u[2] = u24(ph.z); u[3] = u24(ph.w);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x[t] = u[t] < mu[t] ? 1.f : 0.f;
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x[t] = ep.smp == SMP_GAUSS ? mu[t] + rng_normal(ep.rs, e + t) : mu[t];
+              }
+              *reinterpret_cast<float4*>(ep.sample + m * ep.ld_sample + n) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -400,11 +434,17 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, f
   }
 }
 
+static int vec_ok(const EpiParams& ep, int N) {
+  uintptr_t a = (uintptr_t)ep.bias | (uintptr_t)ep.pre | (uintptr_t)ep.mean | (uintptr_t)ep.sample |
+                (ep.rs.mode == MDBN_RNG_BUFFER ? (uintptr_t)ep.rs.seg : 0);
+  return N % 4 == 0 && ep.ld_pre % 4 == 0 && (a & 15) == 0;
+}
 static int up(mdbn_ctx* c, const float* W, int ldw, const float* hb, int B, int V, int H, const float* x, long long ldx,
               float* pre, float* mean, float* sample, long long ldo, const RngSeg& rs, cudaStream_t st) {
   EpiParams ep{};
   ep.bias = hb; ep.act = ACT_SIGMOID; ep.smp = sample ? SMP_BERNOULLI : SMP_NONE; ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
+  ep.vec4 = vec_ok(ep, H);
   return launch_gemm<false, true, EPI_ACT>(c, Operand{x, ldx, false}, Operand{W, ldw, true}, B, H, V, 1, 1 << 30, ep, st);
 }
 static int down(mdbn_ctx* c, const float* W, int ldw, const float* vb, int B, int V, int H, int kind, int noisy,
@@ -415,6 +455,7 @@ static int down(mdbn_ctx* c, const float* W, int ldw, const float* vb, int B, in
   ep.smp = !sample ? SMP_NONE : (kind == MDBN_GRBM ? (noisy ? SMP_GAUSS : SMP_MEAN) : SMP_BERNOULLI);
   ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
+  ep.vec4 = vec_ok(ep, V);
   return launch_gemm<false, false, EPI_ACT>(c, Operand{h, ldh, false}, Operand{W, ldw, false}, B, V, H, 1, 1 << 30, ep,
                                             st);
 }
