@@ -60,7 +60,7 @@ struct Params {
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
   unsigned long long* dbg;   // optional phase timeline (MDBN_SKINNY_TIMING=1), CTA 0 only
   // smem byte offsets
-  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc;
+  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   float* dred = reinterpret_cast<float*>(smem + p.off_dred);  // [NWARP][MB][TR] propdown k-split partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, pl cost
+  float* vbs = reinterpret_cast<float*>(smem + p.off_vb);     // [rows_alloc] visible bias of the owned rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lq = lane >> 2, lr = lane & 3;     // mma fragment coordinates
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 
   // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
   if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);     // start streaming W while the minibatch is gathered
+  for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
   int exact_pred = 1, exact_pred2 = 1;
   for (int e = tid; e < p.rows_alloc * MB; e += NT) {
     int b = e / p.rows_alloc, r = e % p.rows_alloc;
@@ -336,11 +338,17 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       int set = o / (BT * p.CQ), rem = o % (BT * p.CQ);
       int b = rem / p.CQ, qq = rem % p.CQ;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = lane; c < p.n_active; c += 32) {
-        const float4* src = reinterpret_cast<const float4*>(p.part + ((size_t)c * 2 + set) * BT * ldw);
-        float4 t = __ldcg(&src[b * ldw4 + qq]);
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      // up to 8 partials per lane (grids up to 256 CTAs): all loads in flight at once, summed in order
+      float4 t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = lane + 32 * u;
+        t8[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < p.n_active)
+          t8[u] = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)c * 2 + set) * BT * ldw) + b * ldw4 + qq);
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += t8[u].x; s.y += t8[u].y; s.z += t8[u].z; s.w += t8[u].w; }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 #pragma unroll
           for (int w2 = 0; w2 < NWARP; ++w2) sum += dred[((size_t)w2 * MB + b) * p.TR + r];
           const int gi = row0 + j * p.TR + r;
-          const float pre = sum + p.vb[gi];
+          const float pre = sum + vbs[j * p.TR + r];
           if (p.kind == MDBN_GRBM) {
             mean = pre;
             vin = pre;        // mean-field visible: h given v_MEAN (src/rbm.py:669)
@@ -724,7 +732,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 
 struct Geometry {
   int BT, NPW, rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, grid, ldp, ldh, slot_bytes;
-  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc;
+  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
   size_t smem;
   bool ok;
 };
@@ -767,7 +775,8 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
   const size_t hs_b = up128((size_t)MB * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
                vt_b = up128((size_t)MAX_TR * BTS * 4), dred_b = up128((size_t)NWARP * MB * g.TR * 4);
-  const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256;
+  const size_t vb_b = up128((size_t)g.rows_alloc * 4);
+  const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256 + vb_b;
   const size_t smem_max = 227 * 1024;
   const int narr = a.weightcost != 0.f ? 3 : 2;
   if (fixed + (size_t)narr * g.slot_bytes > smem_max) return g;
@@ -783,6 +792,7 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.off_dred = take(dred_b);
   g.off_bars = take(128);
   g.off_misc = take(256);
+  g.off_vb = take(vb_b);
   g.smem = off;
   g.ok = g.smem <= smem_max;
   return g;
@@ -835,7 +845,7 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.TR = g.TR; p.nslots = g.nslots;
   p.ldp = g.ldp; p.ldh = g.ldh; p.slot_bytes = g.slot_bytes;
   p.off_hs = g.off_hs; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vt = g.off_vt; p.off_dred = g.off_dred;
-  p.off_bars = g.off_bars; p.off_misc = g.off_misc;
+  p.off_bars = g.off_bars; p.off_misc = g.off_misc; p.off_vb = g.off_vb;
 
   // scratch: [part | PH | NH | HS | PREX | cost_part]; zero-filled whenever (re)allocated so that
   // padded columns of the [BT][ldw] buffers stay zero
