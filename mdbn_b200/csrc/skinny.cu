@@ -379,13 +379,41 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   };
 
   auto load_hs = [&](const float* src, int ld_src, int nrows_src) {
+    // [BT][ldw] chain state from L2 into the padded shared-memory panel.  float4 loads, four
+    // independent loads in flight per thread (a dependent chain of L2 round trips was 3-7 us here).
     int pred = 1;
-    for (int e = tid; e < BT * ldw; e += NT) {
-      int b = e / ldw, j = e % ldw;
-      float x = 0.f;
-      if (b < nrows_src && j < H) x = __ldcg(&src[(size_t)b * ld_src + j]);
-      hs[b * ldh + j] = x;
-      pred &= ((__float_as_uint(x) & 0x1FFFu) == 0u) ? 1 : 0;
+    const int ldw4 = ldw >> 2, n4 = BT * ldw4;
+    const bool vec = (ld_src & 3) == 0 && (((uintptr_t)src) & 15) == 0;
+    for (int e0 = tid; e0 < n4; e0 += 4 * NT) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * NT;
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n4) {
+          const int b = e / ldw4, j = (e - b * ldw4) * 4;
+          if (b < nrows_src) {
+            const float* sp = src + (size_t)b * ld_src + j;
+            if (vec && j + 3 < H) x[u] = __ldcg(reinterpret_cast<const float4*>(sp));
+            else {
+              if (j < H) x[u].x = __ldcg(sp);
+              if (j + 1 < H) x[u].y = __ldcg(sp + 1);
+              if (j + 2 < H) x[u].z = __ldcg(sp + 2);
+              if (j + 3 < H) x[u].w = __ldcg(sp + 3);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * NT;
+        if (e < n4) {
+          const int b = e / ldw4, j = (e - b * ldw4) * 4;
+          *reinterpret_cast<float4*>(hs + b * ldh + j) = x[u];
+          pred &= (((__float_as_uint(x[u].x) | __float_as_uint(x[u].y) | __float_as_uint(x[u].z) |
+                     __float_as_uint(x[u].w)) & 0x1FFFu) == 0u) ? 1 : 0;
+        }
+      }
     }
     return __syncthreads_and(pred) != 0;      // {0,1} chain states are exact in tf32
   };
