@@ -28,8 +28,6 @@
 namespace mdbn {
 namespace sk {
 
-constexpr int NT = 256;
-constexpr int NWARP = NT / 32;
 constexpr int MAX_SLOTS = 6;
 constexpr int MAX_TR = 32;
 constexpr int MAX_NTD = MAX_TR / 8;
@@ -137,12 +135,14 @@ struct Cfg {
   static constexpr int BTS = MT == 1 ? 24 : 40;  // slab row stride in floats, = 8 or 24 mod 32
 };
 
-template <int BT, int NPW>
+template <int BT, int NPW, int NT>
 __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   using C = Cfg<BT>;
+  constexpr int NWARP = NT / 32;
   constexpr int BTP = C::BTP, MT = C::MT, MB = C::MB, BTS = C::BTS;
-  constexpr int NTD = NPW == 16 ? 2 : MAX_NTD;   // wide layers have short tiles (TR <= 16)
-  constexpr bool ALLOW_DUAL = !(NPW == 16 && MT == 2);   // register budget (plan() routes that case away)
+  constexpr bool WIDE = NPW * NWARP * 8 > 512;   // H > 512: short tiles (TR <= 16)
+  constexpr int NTD = WIDE ? 2 : MAX_NTD;
+  constexpr bool ALLOW_DUAL = !(WIDE && MT == 2);   // register budget (plan() routes that case away)
   extern __shared__ __align__(1024) unsigned char smem[];
   float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [MB][ldh] chain state
   float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows_alloc][BTS]
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
 }
 
 struct Geometry {
-  int BT, NPW, rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, grid, ldp, ldh, slot_bytes;
+  int BT, NPW, NT, rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, grid, ldp, ldh, slot_bytes;
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
   size_t smem;
   bool ok;
@@ -776,13 +776,16 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   const int MT = g.BT > 16 ? 2 : 1, MB = 16 * MT, BTS = MT == 1 ? 24 : 40;
   const bool pcd = a.persistent != nullptr;
   g.CQ = a.ldw / 4;
-  if (g.CQ > NT) return g;
   const int ncols8 = (a.H + 7) & ~7;
-  g.NPW = ncols8 <= 512 ? 8 : 16;
   if (ncols8 > 1024) return g;
-  if (g.NPW == 16 && MT == 2 && pcd) return g;     // register budget of the dual accumulators
+  // 512 threads (16 warps) was measured slower (Gibbs pass 40 vs 31 us): register spills at 128 regs/thread
+  g.NT = 256;
+  if (g.CQ > g.NT) return g;
+  const bool wide = ncols8 > 512;
+  g.NPW = (g.NT == 512) ? (wide ? 8 : 4) : (wide ? 16 : 8);
+  if (wide && MT == 2 && pcd) return g;     // register budget of the dual accumulators
   if (g.CQ <= 32) { g.GW = 1; while (g.GW < g.CQ) g.GW <<= 1; } else g.GW = (g.CQ + 31) / 32 * 32;
-  g.G = NT / g.GW;
+  g.G = g.NT / g.GW;
   g.grid = c->num_sms;
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
   g.rows_alloc = (g.rows_per_cta + 7) & ~7;
@@ -795,14 +798,14 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   tr &= ~7;
   if (tr < 8) return g;
   if (tr > MAX_TR) tr = MAX_TR;
-  if (g.NPW == 16 && tr > 16) tr = 16;
+  if (wide && tr > 16) tr = 16;
   // no point in tiles taller than the slab
   while (tr > 8 && tr - 8 >= g.rows_alloc) tr -= 8;
   g.TR = tr;
   g.slot_bytes = (g.TR * g.ldp * 4 + 127) & ~127;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
   const size_t hs_b = up128((size_t)MB * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
-               vt_b = up128((size_t)MAX_TR * BTS * 4), dred_b = up128((size_t)NWARP * MB * g.TR * 4);
+               vt_b = up128((size_t)MAX_TR * BTS * 4), dred_b = up128((size_t)(g.NT / 32) * MB * g.TR * 4);
   const size_t vb_b = up128((size_t)g.rows_alloc * 4);
   const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256 + vb_b;
   const size_t smem_max = 227 * 1024;
@@ -826,10 +829,10 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   return g;
 }
 
-template <int BT, int NPW>
+template <int BT, int NPW, int NT>
 static int launch(mdbn_ctx* c, const Params& p, const Geometry& g, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kfn = cd_skinny_kernel<BT, NPW>;
+  auto kfn = cd_skinny_kernel<BT, NPW, NT>;
   if (!configured[c->device]) {
     MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[c->device] = true;
@@ -903,10 +906,10 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
   p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;   // needs 32 slots
   int rc = 2;
-  if (g.BT == 10 && g.NPW == 8) rc = sk::launch<10, 8>(c, p, g, st);
-  else if (g.BT == 10 && g.NPW == 16) rc = sk::launch<10, 16>(c, p, g, st);
-  else if (g.BT == 20 && g.NPW == 8) rc = sk::launch<20, 8>(c, p, g, st);
-  else if (g.BT == 20 && g.NPW == 16) rc = sk::launch<20, 16>(c, p, g, st);
+  if (g.BT == 10 && g.NPW == 8) rc = sk::launch<10, 8, 256>(c, p, g, st);
+  else if (g.BT == 10 && g.NPW == 16) rc = sk::launch<10, 16, 256>(c, p, g, st);
+  else if (g.BT == 20 && g.NPW == 8) rc = sk::launch<20, 8, 256>(c, p, g, st);
+  else if (g.BT == 20 && g.NPW == 16) rc = sk::launch<20, 16, 256>(c, p, g, st);
   else set_error("skinny path: no kernel for BT=%d NPW=%d", g.BT, g.NPW);
   if (rc == 0 && p.dbg) {
     unsigned long long t[32];
