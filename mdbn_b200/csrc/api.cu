@@ -154,7 +154,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int path = a->path;
   if (path == MDBN_PATH_AUTO) {
-    if (a->phase == MDBN_PHASE_FULL && skinny_supported(c, *a)) path = MDBN_PATH_SKINNY;
+    if (a->phase == MDBN_PHASE_FULL && (skinny_tc_supported(c, *a) || skinny_supported(c, *a))) path = MDBN_PATH_SKINNY;
     else if (a->tf32 && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;
     else path = MDBN_PATH_GENERIC;
   }
@@ -162,6 +162,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
     case MDBN_PATH_GENERIC:
       return generic_cd_step(c, *a, st);
     case MDBN_PATH_SKINNY:
+      if (skinny_tc_supported(c, *a)) return skinny_tc_cd_step(c, *a, st);     // big layers: tcgen05 edition
       MDBN_CHECK(skinny_supported(c, *a), "cd_step: skinny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B,
                  a->V, a->H, a->ldw, a->phase);
       return skinny_cd_step(c, *a, st);

@@ -159,6 +159,12 @@ CONFIG_SHAPES = [
     ("cfg4_top2_cd1", O.RBM, 24, 3, 20, 1, False, 0.1, 0.9, 0.0, 0.0, 0.0002),
     ("cfg3_dbn_l1", O.RBM, 1000, 1000, 20, 1, False, 0.01, 0.9, 0.0, 0.0, 0.0002),
     ("cfg5_b128_k2", O.RBM, 784, 500, 128, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    # large layers with B <= 16 take the tcgen05 edition of the skinny kernel (skinny_tc.cu)
+    ("tc_ge_cd1_b10", O.GRBM, 19937, 400, 10, 1, False, 0.005, 0.0, 0.01, 0.1, 0.0),
+    ("tc_rbm_4096x256_b16_cd2", O.RBM, 4096, 256, 16, 2, False, 0.1, 0.6, 0.0, 0.0, 0.0002),
+    ("tc_rbm_2100x512_b8_pcd1", O.RBM, 2100, 512, 8, 1, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("tc_grbm_3000x200_b5_cd3", O.GRBM, 3000, 200, 5, 3, False, 0.005, 0.3, 0.02, 0.05, 0.001),
+    ("tc_grbm_5003x96_b13_pcd2", O.GRBM, 5003, 96, 13, 2, True, 0.005, 0.0, 0.01, 0.1, 0.0),
     ("odd_shapes", O.RBM, 77, 13, 7, 3, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
     ("odd_shapes_g", O.GRBM, 131, 30, 3, 2, True, 0.01, 0.3, 0.02, 0.05, 0.001),
 ]
