@@ -57,8 +57,8 @@ int mdbn_create(mdbn_ctx** out, int device) {
   c->device = device;
   c->num_sms = p.multiProcessorCount;
   c->l2_bytes = p.l2CacheSize;
-  MDBN_CUDA(cudaMalloc(&c->barrier, 512));
-  MDBN_CUDA(cudaMemset(c->barrier, 0, 512));
+  MDBN_CUDA(cudaMalloc(&c->barrier, 4096));
+  MDBN_CUDA(cudaMemset(c->barrier, 0, 4096));
   *out = c;
   return 0;
 }

@@ -25,8 +25,9 @@ namespace sktc {
 
 constexpr int NT = 384, NWARP = NT / 32;
 constexpr int NB = 16;                 // MMA N: batch rows padded to 16
-constexpr int STAGE = 32768;           // hi 16 KB | lo 16 KB
-constexpr int MAX_STG = 4;
+constexpr int TILE = 16384;            // one staged W tile (TMA); its lo twin lives in a separate 2-deep ring
+constexpr int MAX_STG = 8;             // hi tiles in flight: sized for HBM latency, not for the MMA hop
+constexpr int NLO = 3;
 constexpr int N_TRANSFORM_WARPS = 6;   // warps 6..11
 constexpr int MAX_SBAR = 6;
 
@@ -120,9 +121,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// D f32, A/B tf32, M = 128, N = 16, B K-major
-__device__ constexpr uint32_t make_idesc(bool a_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(NB >> 3) << 17) |
+// D f32, A/B tf32, M = 128, N = n (16/32/48: stacked panels), B K-major
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
 }
 // activation panel [16][KP], K-major, no swizzle: 8x4-float core matrices, 128 B apart along K,
@@ -175,7 +176,6 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   const int rows8 = (rows + 7) & ~7;
   const int nrq = (rows8 + 31) >> 5;
   const int tail8 = rows8 - 32 * (nrq - 1);            // rows (multiple of 8) in the last 32-row quarter
-  const int ng = (rows8 + 127) >> 7;
   const int nch = KH >> 5;
   const int q = tid % p.GW, g_ = tid / p.GW;
   const bool col_ok = g_ < p.G && q < p.CQ;
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
 
   // barrier addresses
   const uint32_t b_full = smem_u32(bars), b_ready = b_full + 8 * MAX_STG, b_empty = b_ready + 8 * MAX_STG;
-  const uint32_t b_accfull = b_empty + 8 * MAX_STG, b_dfull = b_accfull + 8, b_dfree = b_dfull + 16;
+  const uint32_t b_lofree = b_empty + 8 * MAX_STG;
+  const uint32_t b_accfull = b_lofree + 8 * NLO, b_dfull = b_accfull + 8, b_dfree = b_dfull + 16;
   const uint32_t b_stats = b_dfree + 16;
 
   int dbg_i = 0;
@@ -194,6 +195,13 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
       p.dbg[dbg_i++] = t;
     }
   };
+  auto stamp = [&](int role, uint32_t n) {      // per-stage role timeline of the first 16 stages (debug)
+    if (p.dbg && cta == 0 && n < 16) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[32 + role * 16 + n] = t;
+    }
+  };
   mark();
 
   if (tid == 0) {
@@ -202,13 +210,14 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
       mbar_init(b_ready + 8 * i, N_TRANSFORM_WARPS);
       mbar_init(b_empty + 8 * i, 1);
     }
+    for (int i = 0; i < NLO; ++i) mbar_init(b_lofree + 8 * i, 1);
     mbar_init(b_accfull, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(b_dfull + 8 * i, 1); mbar_init(b_dfree + 8 * i, 4); }
     for (int i = 0; i < MAX_SBAR; ++i) mbar_init(b_stats + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -241,7 +250,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   (void)__syncthreads_and(ex1);     // rounded inputs beyond +-2048 keep only their tf32 part in the monitor
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_acc = tmem, t_acc2 = tmem + nmt * NB, t_d = tmem + 2 * nmt * NB;
+  // TMEM columns.  Per 128-column m-tile of the propup: [0,48) = A_hi x {src_lo, src, x}, [48,80) = A_lo x {src, x};
+  // per propdown accumulator: [0,32) = A_hi x {h_lo, h}, [32,48) = A_lo x h.
+  constexpr int UC = 80, DC = 48;
+  const uint32_t t_d = tmem + nmt * UC;
   mark();   // gather done
 
   // ring / pipeline state (each role keeps its own counters; the schedules are deterministic)
@@ -259,16 +271,22 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   };
 
   // lo twin of one staged 16 KB tile (transform warps)
-  auto transform_stage = [&](int slot) {
-    float4* hi = reinterpret_cast<float4*>(smem + (size_t)slot * STAGE);
-    float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * STAGE + STAGE / 2);
-    for (int e = tid - (NT - 32 * N_TRANSFORM_WARPS); e < STAGE / 32; e += 32 * N_TRANSFORM_WARPS) {
+  auto transform_stage = [&](uint32_t n) {
+    const int slot = n % nstg, ls = n % NLO;
+    mbar_wait(b_full + 8 * slot, (n / nstg) & 1);
+    if (tid == NT - 32 * N_TRANSFORM_WARPS) stamp(1, n);
+    mbar_wait(b_lofree + 8 * ls, ((n / NLO) & 1) ^ 1);
+    if (tid == NT - 32 * N_TRANSFORM_WARPS) stamp(2, n);
+    const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)slot * TILE);
+    float4* lo = reinterpret_cast<float4*>(smem + (size_t)(nstg + ls) * TILE);
+    for (int e = tid - (NT - 32 * N_TRANSFORM_WARPS); e < TILE / 16; e += 32 * N_TRANSFORM_WARPS) {
       const float4 x = hi[e];
       lo[e] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(b_ready + 8 * slot);
+    if (tid == NT - 32 * N_TRANSFORM_WARPS) stamp(3, n);
   };
 
   // =========================================================================================
@@ -283,7 +301,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
             for (int mt = 0; mt < nmt; ++mt, ++stage_n) {
               const int slot = stage_n % nstg;
               mbar_wait(b_empty + 8 * slot, ((stage_n / nstg) & 1) ^ 1);
-              const uint32_t dst = ring + slot * STAGE, bar = b_full + 8 * slot;
+              const uint32_t dst = ring + slot * TILE, bar = b_full + 8 * slot;
+              stamp(0, stage_n);
               mbar_expect_tx(bar, 4u * nr8 * 128u);
               if (nr8 == 32) {
 #pragma unroll
@@ -298,58 +317,80 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
         }
       } else if (warp == 1) {
         if (lane == 0) {
-          const uint32_t idesc = make_idesc(true);
-          const uint32_t s_hi = smem_u32(src_hi), s_lo = smem_u32(src_lo), s_x = smem_u32(xp);
+          // B operands: stacked panels [src_lo | src | x]; src_exact drops the lo panel, dual adds x
+          const uint32_t s_b1 = smem_u32(src_exact ? src_hi : src_lo), s_b2 = smem_u32(src_hi);
+          const int n1 = (src_exact ? 16 : 32) + (dual ? 16 : 0), n2 = dual ? 32 : 16;
+          const int c1 = src_exact ? 16 : 0;
+          const uint32_t id1 = make_idesc(true, n1), id2 = make_idesc(true, n2);
+          const uint64_t db1 = make_desc(s_b1, 128, KR * 32, 0), db2 = make_desc(s_b2, 128, KR * 32, 0);
           for (int rq = 0; rq < nrq; ++rq) {
             const int nkk = ((rq == nrq - 1) ? tail8 : 32) >> 3;
             for (int mt = 0; mt < nmt; ++mt, ++stage_n) {
               const int slot = stage_n % nstg;
-              mbar_wait(b_ready + 8 * slot, (stage_n / nstg) & 1);
+              const uint32_t a0 = ring + slot * TILE, l0 = ring + (nstg + stage_n % NLO) * TILE;
+              // the hi products only need the TMA tile: they run while the transform warps make the lo twin
+              mbar_wait(b_full + 8 * slot, (stage_n / nstg) & 1);
+              stamp(4, stage_n);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a0 = ring + slot * STAGE;
-              for (int kk = 0; kk < nkk; ++kk) {
-                const int k = rq * 32 + kk * 8;
-                const uint64_t a_hi = make_desc(a0 + kk * 1024, 4096, 512, 1);
-                const uint64_t a_lo = make_desc(a0 + STAGE / 2 + kk * 1024, 4096, 512, 1);
-                const uint64_t b_hi = make_desc(s_hi + (k >> 2) * 128, 128, KR * 32, 0);
-                const uint32_t acc = (rq == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32(t_acc + mt * NB, a_hi, b_hi, idesc, acc);
-                umma_tf32(t_acc + mt * NB, a_lo, b_hi, idesc, 1u);
-                if (!src_exact) umma_tf32(t_acc + mt * NB, a_hi, make_desc(s_lo + (k >> 2) * 128, 128, KR * 32, 0), idesc, 1u);
-                if (dual) {
-                  const uint64_t x_hi = make_desc(s_x + (k >> 2) * 128, 128, KR * 32, 0);
-                  umma_tf32(t_acc2 + mt * NB, a_hi, x_hi, idesc, acc);
-                  umma_tf32(t_acc2 + mt * NB, a_lo, x_hi, idesc, 1u);
-                }
+              // descriptors differ only in their start-address field: +64 (1024 B >> 4) per k-step on the
+              // W tile, +16 (2 core matrices of 128 B) on the panels
+              {
+                const uint64_t ad = make_desc(a0, 4096, 512, 1);
+                const uint64_t bd = db1 + (uint64_t)(rq * 64);
+                const uint32_t acc0 = rq == 0 ? 0u : 1u;
+                for (int kk = 0; kk < nkk; ++kk)
+                  umma_tf32(tmem + mt * UC + c1, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 16), id1, kk == 0 ? acc0 : 1u);
+              }
+              mbar_wait(b_ready + 8 * slot, (stage_n / nstg) & 1);
+              stamp(5, stage_n);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              {
+                const uint64_t ad = make_desc(l0, 4096, 512, 1);
+                const uint64_t bd = db2 + (uint64_t)(rq * 64);
+                const uint32_t acc0 = rq == 0 ? 0u : 1u;
+                for (int kk = 0; kk < nkk; ++kk)
+                  umma_tf32(tmem + mt * UC + 48, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 16), id2, kk == 0 ? acc0 : 1u);
               }
               umma_commit(b_empty + 8 * slot);
+              umma_commit(b_lofree + 8 * (stage_n % NLO));
             }
           }
           umma_commit(b_accfull);
         }
       } else if (warp >= NWARP - N_TRANSFORM_WARPS) {
         for (int rq = 0; rq < nrq; ++rq)
-          for (int mt = 0; mt < nmt; ++mt, ++stage_n) {
-            const int slot = stage_n % nstg;
-            mbar_wait(b_full + 8 * slot, (stage_n / nstg) & 1);
-            transform_stage(slot);
-          }
+          for (int mt = 0; mt < nmt; ++mt, ++stage_n) transform_stage(stage_n);
       } else {
         // epilogue warps 2..5: accumulators -> this CTA's partial [B][ldw] in global scratch
         mbar_wait(b_accfull, ph_acc);
         ph_acc ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
-        for (int set = 0; set < (dual ? 2 : 1); ++set) {
-          float* dst = p.part + ((size_t)cta * 2 + set) * B * ldw;
-          for (int mt = 0; mt < nmt; ++mt) {
-            uint32_t r[16];
-            tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (set * nmt + mt) * NB, r);
-            const int j = mt * 128 + quarter * 32 + lane;
+        for (int mt = 0; mt < nmt; ++mt) {
+          const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + mt * UC;
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(tb + 16, r0);                     // A_hi x src
+          tmem_ld16(tb + 48, r1);                     // A_lo x src
+          if (!src_exact) tmem_ld16(tb, r2);          // A_hi x src_lo
+          const int j = mt * 128 + quarter * 32 + lane;
+          float* dst = p.part + ((size_t)cta * 2) * B * ldw;
+          if (j < ldw) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+              if (b < B) {
+                float v = __uint_as_float(r1[b]);
+                if (!src_exact) v += __uint_as_float(r2[b]);
+                __stcg(dst + (size_t)b * ldw + j, __uint_as_float(r0[b]) + v);
+              }
+          }
+          if (dual) {
+            tmem_ld16(tb + 32, r0);                   // A_hi x x
+            tmem_ld16(tb + 64, r1);                   // A_lo x x
+            dst += (size_t)B * ldw;
             if (j < ldw) {
 #pragma unroll
               for (int b = 0; b < NB; ++b)
-                if (b < B) __stcg(dst + (size_t)b * ldw + j, __uint_as_float(r[b]));
+                if (b < B) __stcg(dst + (size_t)b * ldw + j, __uint_as_float(r0[b]) + __uint_as_float(r1[b]));
             }
           }
         }
@@ -363,16 +404,21 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   // propdown pass: v[b, i] = act( sum_j W[i][j] h[b][j] + vb[i] ) for this CTA's rows, into the vin panels
   // =========================================================================================
   float cost_acc = 0.f;
-  auto d_pass = [&](bool h_exact, const RngSeg& rs_v, bool last) {
+  // tensor groups of 128 rows; a remainder of <= 32 rows after at least one full group goes to SIMT
+  const int ng_full = rows8 >> 7, rem_rows = rows8 - 128 * ng_full;
+  const bool simt_tail = ng_full > 0 && rem_rows > 0 && rem_rows <= 32;
+  const int ngt = ng_full + ((rem_rows > 0 && !simt_tail) ? 1 : 0);
+  const int tail_r0 = 128 * ng_full, tail_n = simt_tail ? max(0, rows - tail_r0) : 0;
+  auto d_pass = [&](bool h_exact, const RngSeg& rs_v, bool last, const float* hsrc, int hld) {
     if (rows > 0) {
       if (warp == 0) {
         if (lane == 0) {
-          for (int g = 0; g < ng; ++g) {
+          for (int g = 0; g < ngt; ++g) {
             const int gr8 = min(128, rows8 - 128 * g), n32 = gr8 >> 5, t8 = (gr8 & 31) >> 3;
             for (int c = 0; c < nch; ++c, ++stage_n) {
               const int slot = stage_n % nstg;
               mbar_wait(b_empty + 8 * slot, ((stage_n / nstg) & 1) ^ 1);
-              const uint32_t dst = ring + slot * STAGE, bar = b_full + 8 * slot;
+              const uint32_t dst = ring + slot * TILE, bar = b_full + 8 * slot;
               mbar_expect_tx(bar, (uint32_t)gr8 * 128u);
               for (int t = 0; t < n32; ++t) tma_load_2d(dst + t * 4096, &tmK32, bar, 32 * c, row0 + 128 * g + 32 * t);
               for (int u = 0; u < t8; ++u)
@@ -382,75 +428,110 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
         }
       } else if (warp == 1) {
         if (lane == 0) {
-          const uint32_t idesc = make_idesc(false);
-          const uint32_t s_h = smem_u32(hp), s_hlo = smem_u32(hplo);
-          for (int g = 0; g < ng; ++g) {
+          const uint32_t s_b1 = smem_u32(h_exact ? hp : hplo), s_b2 = smem_u32(hp);
+          const int c1 = h_exact ? 16 : 0;
+          const uint32_t id1 = make_idesc(false, h_exact ? 16 : 32), id2 = make_idesc(false, 16);
+          const uint64_t db1 = make_desc(s_b1, 128, KH * 32, 0), db2 = make_desc(s_b2, 128, KH * 32, 0);
+          for (int g = 0; g < ngt; ++g) {
             const int di = g & 1;
             if (n_d[di] > 0) mbar_wait(b_dfree + 8 * di, (n_d[di] - 1) & 1);    // epilogue drained the previous use
             for (int c = 0; c < nch; ++c, ++stage_n) {
               const int slot = stage_n % nstg;
+              const uint32_t a0 = ring + slot * TILE, l0 = ring + (nstg + stage_n % NLO) * TILE;
+              mbar_wait(b_full + 8 * slot, (stage_n / nstg) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              {
+                const uint64_t ad = make_desc(a0, 16, 1024, 2);       // +2 (32 B >> 4) per k-step along the swizzled row
+                const uint64_t bd = db1 + (uint64_t)(c * 64);
+                const uint32_t acc0 = c == 0 ? 0u : 1u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_tf32(t_d + di * DC + c1, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 16), id1, kk == 0 ? acc0 : 1u);
+              }
               mbar_wait(b_ready + 8 * slot, (stage_n / nstg) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a0 = ring + slot * STAGE;
+              {
+                const uint64_t ad = make_desc(l0, 16, 1024, 2);
+                const uint64_t bd = db2 + (uint64_t)(c * 64);
+                const uint32_t acc0 = c == 0 ? 0u : 1u;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const int k = c * 32 + kk * 8;
-                const uint64_t a_hi = make_desc(a0 + kk * 32, 16, 1024, 2);
-                const uint64_t a_lo = make_desc(a0 + STAGE / 2 + kk * 32, 16, 1024, 2);
-                const uint64_t b_hi = make_desc(s_h + (k >> 2) * 128, 128, KH * 32, 0);
-                umma_tf32(t_d + di * NB, a_hi, b_hi, idesc, (c == 0 && kk == 0) ? 0u : 1u);
-                umma_tf32(t_d + di * NB, a_lo, b_hi, idesc, 1u);
-                if (!h_exact) umma_tf32(t_d + di * NB, a_hi, make_desc(s_hlo + (k >> 2) * 128, 128, KH * 32, 0), idesc, 1u);
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_tf32(t_d + di * DC + 32, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 16), id2, kk == 0 ? acc0 : 1u);
               }
               umma_commit(b_empty + 8 * slot);
+              umma_commit(b_lofree + 8 * (stage_n % NLO));
             }
             umma_commit(b_dfull + 8 * di);
             n_d[di]++;
           }
         }
       } else if (warp >= NWARP - N_TRANSFORM_WARPS) {
-        for (int g = 0; g < ng; ++g)
-          for (int c = 0; c < nch; ++c, ++stage_n) {
-            const int slot = stage_n % nstg;
-            mbar_wait(b_full + 8 * slot, (stage_n / nstg) & 1);
-            transform_stage(slot);
-          }
+        for (int g = 0; g < ngt; ++g)
+          for (int c = 0; c < nch; ++c, ++stage_n) transform_stage(stage_n);
       } else {
         // epilogue warps: bias, activation, sampling (src/rbm.py:226-240 / :650-660) -> vin panels
         const int quarter = warp & 3;
-        for (int g = 0; g < ng; ++g) {
+        auto emit = [&](int r, int b, float sum) {
+          float vin = 0.f, mean = 0.f;
+          if (b < B) {
+            const float pre = sum + vbs[r];
+            if (p.kind == MDBN_GRBM) {
+              mean = pre;
+              vin = pre;          // mean-field visible: h given v_MEAN (src/rbm.py:669)
+            } else {
+              mean = sigmoidf_(pre);
+              vin = rng_uniform(rs_v, (long long)b * V + row0 + r) < mean ? 1.f : 0.f;
+            }
+            if (last && !p.pcd) {
+              const float t = v0p[poff(b, r, KR)];
+              if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t; cost_acc += d * d; }   // :697
+              else cost_acc += t * softplusf_(-pre) + (1.f - t) * softplusf_(pre);                  // :479-480
+            }
+          }
+          const int o = poff(b, r, KR);
+          vinp[o] = vin;
+          vinlo[o] = tf32_lo(vin);
+          if (last) nvp[o] = mean;
+        };
+        // the few rows beyond the last full 128-row group: plain fp32 dot products, done while the
+        // tensor pipeline streams the full groups (these warps would otherwise wait)
+        for (int rr = warp - 2; rr < tail_n; rr += 4) {
+          const int r = tail_r0 + rr;
+          const float* wrow = p.W + (size_t)(row0 + r) * ldw;
+          float w[16];                               // H <= 512: this lane's columns lane, lane+32, ...
+#pragma unroll
+          for (int t = 0; t < 16; ++t) w[t] = (lane + 32 * t < H) ? __ldg(wrow + lane + 32 * t) : 0.f;
+          float mine = 0.f;
+          for (int b = 0; b < B; ++b) {
+            const float* hrow = hsrc + (size_t)b * hld;
+            float hv[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) hv[t] = (lane + 32 * t < H) ? __ldcg(hrow + lane + 32 * t) : 0.f;
+            float a = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) a = fmaf(hv[t], w[t], a);
+            a = warp_sum(a);
+            if (lane == b) mine = a;
+          }
+          if (lane < NB) emit(r, lane, mine);
+        }
+        for (int g = 0; g < ngt; ++g) {
           const int di = g & 1;
           mbar_wait(b_dfull + 8 * di, n_d[di] & 1);
           n_d[di]++;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t r16[16];
-          tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + 2 * nmt * NB + di * NB, r16);
+          const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + nmt * UC + di * DC;
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(tb + 16, r0);                     // A_hi x h
+          tmem_ld16(tb + 32, r1);                     // A_lo x h
+          if (!h_exact) tmem_ld16(tb, r2);            // A_hi x h_lo
           const int r = 128 * g + quarter * 32 + lane;
           if (r < rows) {
-            const int gi = row0 + r;
-            const float vbv = vbs[r];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-              float vin = 0.f, mean = 0.f;
-              if (b < B) {
-                const float pre = __uint_as_float(r16[b]) + vbv;
-                if (p.kind == MDBN_GRBM) {
-                  mean = pre;
-                  vin = pre;          // mean-field visible: h given v_MEAN (src/rbm.py:669)
-                } else {
-                  mean = sigmoidf_(pre);
-                  vin = rng_uniform(rs_v, (long long)b * V + gi) < mean ? 1.f : 0.f;
-                }
-                if (last && !p.pcd) {
-                  const float t = v0p[poff(b, r, KR)];
-                  if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t; cost_acc += d * d; }   // :697
-                  else cost_acc += t * softplusf_(-pre) + (1.f - t) * softplusf_(pre);                  // :479-480
-                }
-              }
-              const int o = poff(b, r, KR);
-              vinp[o] = vin;
-              vinlo[o] = tf32_lo(vin);
-              if (last) nvp[o] = mean;
+              float v = __uint_as_float(r1[b]);
+              if (!h_exact) v += __uint_as_float(r2[b]);
+              emit(r, b, __uint_as_float(r0[b]) + v);
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -458,6 +539,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(b_dfree + 8 * di);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
     }
     __syncthreads();
@@ -578,7 +660,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
     const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
     const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s);
     const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s);
-    d_pass(h_exact, rs_v, last);
+    d_pass(h_exact, rs_v, last, (s == 0 && p.pcd) ? p.P : p.HS, (s == 0 && p.pcd) ? H : ldw);
     u_pass(vinp, vinlo, p.kind == MDBN_RBM, false);
     if (last) mark();
     if (last && !p.pcd) {
@@ -597,7 +679,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   {
     const int narr = p.wc != 0.f ? 3 : 2;
     const int TRS = 8, slot_s = (TRS * ldw * 4 + 127) & ~127;
-    int depth = (nstg * STAGE) / (narr * slot_s);
+    int depth = ((nstg + NLO) * TILE) / (narr * slot_s);
     depth = depth > MAX_SBAR ? MAX_SBAR : depth;
     const int ntiles_s = (rows + TRS - 1) / TRS;
     uint32_t sphase = 0;
@@ -712,7 +794,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_tc_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
   if (tid == 0) {
     __threadfence();
@@ -782,20 +864,21 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.KH = (ncols8 + 31) & ~31;
   g.nmt = (ncols8 + 127) / 128;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
-  const size_t hp_b = up128((size_t)NB * g.KH * 4), rp_b = up128((size_t)NB * g.KR * 4), vb_b = up128((size_t)g.KR * 4);
+  const size_t hp_b = (size_t)NB * g.KH * 4, rp_b = (size_t)NB * g.KR * 4, vb_b = up128((size_t)g.KR * 4);   // KH, KR % 32 == 0
   const size_t fixed = 2 * hp_b + 6 * rp_b + vb_b + 512 + 512;
   const size_t smem_max = 227 * 1024;
-  if (fixed + 2 * (size_t)STAGE > smem_max) return g;
-  g.nstg = (int)((smem_max - fixed) / STAGE);
+  if (fixed + (size_t)(2 + NLO) * TILE > smem_max) return g;
+  g.nstg = (int)((smem_max - fixed) / TILE) - NLO;
   if (g.nstg > MAX_STG) g.nstg = MAX_STG;
   // the statistics pass reuses the ring: W and S (and W_snap) tiles of 8 rows must fit at least once
   const int narr = a.weightcost != 0.f ? 3 : 2;
-  if ((size_t)narr * ((8 * a.ldw * 4 + 127) & ~127) > (size_t)g.nstg * STAGE) return g;
-  size_t off = (size_t)g.nstg * STAGE;
+  if ((size_t)narr * ((8 * a.ldw * 4 + 127) & ~127) > (size_t)(g.nstg + NLO) * TILE) return g;
+  size_t off = (size_t)(g.nstg + NLO) * TILE;
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return (int)o; };
-  g.off_hp = take(hp_b); g.off_hplo = take(hp_b);
-  g.off_v0 = take(rp_b); g.off_v0lo = take(rp_b); g.off_x = take(rp_b);
-  g.off_vin = take(rp_b); g.off_vinlo = take(rp_b); g.off_nv = take(rp_b);
+  // stacked-N operands: [lo | hi | x] panels are contiguous so one MMA covers several of them
+  g.off_hplo = take(hp_b); g.off_hp = take(hp_b);
+  g.off_v0lo = take(rp_b); g.off_v0 = take(rp_b); g.off_x = take(rp_b);
+  g.off_vinlo = take(rp_b); g.off_vin = take(rp_b); g.off_nv = take(rp_b);
   g.off_vb = take(vb_b);
   g.off_bars = take(512);
   g.off_misc = take(512);
@@ -821,8 +904,10 @@ static int launch(mdbn_ctx* c, const CUtensorMap* tms, const Params& p, const Ge
 }  // namespace sktc
 
 bool skinny_tc_supported(const mdbn_ctx* c, const mdbn_cd_args& a) {
-  static const bool off = getenv("MDBN_NO_SKINNY_TC") != nullptr;
-  return !off && sktc::plan(c, a).ok;
+  // opt-in (MDBN_SKINNY_TC=1): fp32-exact via split TF32, but measured slower than the SIMT kernel — for a
+  // 16-wide N every tcgen05.mma re-reads 4 KB of A from shared memory (~130 clk), see DESIGN.md
+  static const bool on = getenv("MDBN_SKINNY_TC") != nullptr;
+  return on && sktc::plan(c, a).ok;
 }
 
 int skinny_tc_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
@@ -886,12 +971,18 @@ int skinny_tc_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   MDBN_TRY(make_map(&tms[3], a.W, a.V, a.ldw, 8, false));
   int rc = g.BT == 10 ? launch<10>(c, tms, p, g, st) : launch<16>(c, tms, p, g, st);
   if (rc == 0 && p.dbg) {
-    unsigned long long t[32];
+    unsigned long long t[32 + 6 * 16];
     MDBN_CUDA(cudaStreamSynchronize(st));
     MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[skinny-tc timeline us] V=%d H=%d B=%d k=%d:", a.V, a.H, a.B, a.k);
+    fprintf(stderr, "[skinny-tc timeline us] V=%d H=%d B=%d k=%d nstg=%d:", a.V, a.H, a.B, a.k, g.nstg);
     for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
     fprintf(stderr, "\n");
+    const char* names[6] = {"tma issue", "xform full", "xform lofree", "xform done", "mma full", "mma ready"};
+    for (int r = 0; r < 6; ++r) {
+      fprintf(stderr, "   %-12s", names[r]);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " %6.2f", (double)(t[32 + r * 16 + i] - t[0]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
   }
   return rc;
 }
