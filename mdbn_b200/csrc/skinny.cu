@@ -3,34 +3,35 @@
 // Regime: batch 10-20 on 10^2..2*10^4-wide layers is 0.36*B flop/byte ->
 // bound by streaming W, not by math.  Design:
 //   * every CTA owns a contiguous slab of W rows (visible units) for the whole step;
-//   * W row tiles are staged in shared memory by 1-D bulk async copies
-//     (cp.async.bulk -> UBLKCP, one per tile: the TMA op rate, ~150 ns per copy per SM, rules
-//     out per-row copies) completing on mbarriers;
-//   * the two skinny GEMMs run on the tensor cores as mma.sync m16n8k8 TF32 with the fp32
-//     operands split hi + lo (3 MMAs per product: hi*hi + lo*hi + hi*lo), which keeps fp32-level
-//     accuracy (the 1e-5 parity bar) at a fraction of the issue slots of FFMA + shuffle
-//     reductions (the tcgen05 shapes, M >= 64, do not fit a 10-20 row batch);
-//   * pass 0      : partial  v0 W          (and round(v0) W for the pseudo-likelihood)
+//   * W row tiles are staged in shared memory by TMA (cp.async.bulk.tensor.2d, boxes of 32 columns x
+//     R rows, 128-byte swizzle) completing on mbarriers, a ring of <= 56 KB stages.  The swizzle is
+//     what makes BOTH access patterns of the step bank-conflict free from one copy of the tile:
+//       propup   (thread = column quad, walks rows)   -> the 8 quads of a box row hit 8 distinct 16-byte
+//                                                        bank groups
+//       propdown (lane = ROW, walks the columns)       -> the 8 rows of an octet hit 8 distinct groups
+//     With lane = row a propdown dot product lives in ONE thread: no cross-lane reduction at all (the
+//     shuffle reductions / mma.sync fragments of the earlier versions were the bottleneck);
+//   * pass 0      : partial  v0 W          (and round(v0) W for the pseudo-likelihood, sharing the W reads)
 //   * pass 1..k   : FUSED propdown + propup from the SAME staged tile: v_i = h . W[i,:] is
-//     complete inside the owning CTA (no cross-CTA traffic), its bias/sigmoid/Bernoulli
-//     epilogue runs in place and the tile is immediately reused for  h' += v_i W[i,:];
-//     so a Gibbs step reads W once, not twice;
+//     complete inside the owning CTA, its bias/sigmoid/Bernoulli epilogue runs in place and the tile is
+//     immediately reused for  h' += v_i W[i,:];  a Gibbs step reads W once, not twice;
 //   * hidden pre-activations need all rows: per-CTA partials -> global scratch -> grid
 //     barrier -> each CTA reduces a slice in fixed order (deterministic) + bias + sigmoid +
 //     sample -> grid barrier -> every CTA reloads the full [B,H] hidden state;
 //   * last pass  : statistics + lambda_1/lambda_2/momentum update fused: W and W_speed tiles
 //     are read once and written once; v0 and nv slabs never left shared memory.
-// HBM traffic per step: (k+1) reads of W + read W,S + write W,S (+ read W_snap) versus the
-// (2k+1)+4 of an unfused implementation.
+// All arithmetic is plain fp32 FFMA.  HBM traffic per step: (k+1) reads of W + read W,S + write W,S
+// (+ read W_snap) versus the (2k+1)+4 of an unfused implementation.
+#include <cuda.h>
 #include <stdlib.h>
 #include "ctx.h"
 
 namespace mdbn {
 namespace sk {
 
+constexpr int NT = 256;
+constexpr int NWARP = NT / 32;
 constexpr int MAX_SLOTS = 6;
-constexpr int MAX_TR = 32;
-constexpr int MAX_NTD = MAX_TR / 8;
 
 struct Params {
   float *W, *S;
@@ -50,13 +51,14 @@ struct Params {
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
   // geometry
-  int rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, ldp, ldh, slot_bytes;
+  int rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, ldh, slot_bytes, ring_bytes;
   // global scratch
   float* part;        // [n_active][2][BT][ldw]
   float *PH, *NH, *HS, *PREX;   // [BT][ldw], zero-initialised, padded columns never written
   float* cost_part;   // [gridDim]
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
   unsigned long long* dbg;   // optional phase timeline (MDBN_SKINNY_TIMING=1), CTA 0 only
+  int dbg_flags;             // MDBN_SKINNY_DEBUG: skip parts of the passes (timing experiments only; results are wrong)
   // smem byte offsets
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
 };
@@ -73,6 +75,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -105,76 +114,37 @@ __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long
   __syncthreads();
 }
 
-// ---- split-TF32 tensor-core helpers -------------------------------------------------
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  // hi = x truncated to tf32 (what the tensor core would do anyway), lo = exact remainder, itself
-  // truncated by the hardware: |x - hi - tf32(lo)| <= 2^-21 |x|.  Bit masks, not cvt.rna: the
-  // conversions run on the quarter-rate XU pipe and were the bottleneck of this loop.
-  hi = __float_as_uint(x) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// c += A * B with A = a_hi + a_lo, B = b_hi + b_lo (lo*lo dropped: 2^-22 relative)
-__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                       uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma_tf32(c, al, bh0, bh1);
-  mma_tf32(c, ah, bl0, bl1);
-  mma_tf32(c, ah, bh0, bh1);
-}
-
 template <int BT>
-struct Cfg {
-  static constexpr int BTP = (BT + 3) / 4 * 4;
-  static constexpr int MT = BT > 16 ? 2 : 1;     // 16-row m-tiles of the batch
-  static constexpr int MB = 16 * MT;             // batch rows seen by the MMAs (zero padded)
-  static constexpr int BTS = MT == 1 ? 24 : 40;  // slab row stride in floats, = 8 or 24 mod 32
-};
-
-template <int BT, int NPW, int NT>
-__global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
-  using C = Cfg<BT>;
-  constexpr int NWARP = NT / 32;
-  constexpr int BTP = C::BTP, MT = C::MT, MB = C::MB, BTS = C::BTS;
-  constexpr bool WIDE = NPW * NWARP * 8 > 512;   // H > 512: short tiles (TR <= 16)
-  constexpr int NTD = WIDE ? 2 : MAX_NTD;
-  constexpr bool ALLOW_DUAL = !(WIDE && MT == 2);   // register budget (plan() routes that case away)
+__global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant__ CUtensorMap tmR,
+                                                          const __grid_constant__ CUtensorMap tm8, const Params p) {
+  constexpr int BTP = (BT + 3) / 4 * 4, BTS = BTP;
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [MB][ldh] chain state
+  float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [BT][ldh] chain state, zero padded to nbox*32 columns
   float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows_alloc][BTS]
   float* nvs = reinterpret_cast<float*>(smem + p.off_nv);     // [rows_alloc][BTS]
-  float* vt = reinterpret_cast<float*>(smem + p.off_vt);      // [TR][BTS] visible tile -> propup input
-  float* dred = reinterpret_cast<float*>(smem + p.off_dred);  // [NWARP][MB][TR] propdown k-split partials
+  float* vt = reinterpret_cast<float*>(smem + p.off_vt);      // [R][BTS] visible tile -> propup input
+  float* dred = reinterpret_cast<float*>(smem + p.off_dred);  // [NWARP * 32/R][BT][R] propdown column-split partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, pl cost
   float* vbs = reinterpret_cast<float*>(smem + p.off_vb);     // [rows_alloc] visible bias of the owned rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lq = lane >> 2, lr = lane & 3;     // mma fragment coordinates
   const int cta = blockIdx.x;
-  const int ldw = p.ldw, ldp = p.ldp, ldp4 = ldp >> 2, ldh = p.ldh;
+  const int ldw = p.ldw, ldh = p.ldh, R = p.R, nbox = p.nbox;
   const int B = p.B, V = p.V, H = p.H;
   const int row0 = cta * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, V - row0));
-  const int ntiles = (rows + p.TR - 1) / p.TR;
-  const int ncols8 = (H + 7) & ~7;
-  // SIMT mapping of the statistics pass: thread -> (row group g, column quad q)
+  const int ntiles = (rows + R - 1) / R;
+  const int box_bytes = R * 128;
+  // propup / statistics mapping: thread -> (row group g, column quad q)
   const int q = tid % p.GW, g = tid / p.GW;
   const bool col_ok = g < p.G && q < p.CQ;
+  // propdown mapping: lane -> (row of the tile, which of the 32/R boxes handled together)
+  const int drow = lane & (R - 1), dsub = lane / R, SUBS = 32 / R;
   unsigned long long bar_target = 0;
   uint32_t phase_bits = 0;
-  int dbg_i = 0, dbg_j = 16;
-  auto mark2 = [&]() {
-    if (p.dbg && cta == 0 && tid == 0 && dbg_j < 32) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.dbg[dbg_j++] = t;
-    }
-  };
+  int dbg_i = 0;
+  const int F = p.dbg_flags;
   auto mark = [&]() {
     if (p.dbg && cta == 0 && tid == 0) {
       unsigned long long t;
@@ -188,23 +158,34 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     for (int i = 0; i < MAX_SLOTS; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the ring once: the pad columns [ldw, ldp) of every staged row are never written by the
-  // copies and are read (times zero) by the last 8-column fragment
-  for (int e = tid; e < p.nslots * (p.slot_bytes >> 4); e += NT)
-    reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int e = tid; e < MB * ldh; e += NT) hs[e] = 0.f;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int e = tid; e < BT * ldh; e += NT) hs[e] = 0.f;
   __syncthreads();
 
   // ---- tile pipeline --------------------------------------------------------------
-  // job j of a pass loads `narr` arrays (W [, S [, Wsnap]]) of tile j into consecutive slots, one
-  // bulk copy per row (padded destination stride).  Called by all lanes of warp 0.
-  auto issue = [&](int j, int narr, int depth, int tr, int slot_b) {      // lane 0 of warp 0
+  // W-only passes: stage j = rows [j*R, j*R+R) x all columns as nbox swizzled boxes (TMA).  lane 0 of warp 0.
+  auto issue = [&](int j, int depth) {
+    const int r0 = j * R;
+    if (r0 >= rows || lane != 0) return;
+    const int st = j % depth;
+    const int nr8 = (min(R, rows - r0) + 7) & ~7;
+    uint64_t* bar = &bars[st];
+    unsigned char* dst = smem + (size_t)st * p.slot_bytes;
+    mbar_expect_tx(bar, (uint32_t)nbox * nr8 * 128u);
+    if (nr8 == R) {
+      for (int bx = 0; bx < nbox; ++bx) tma_load_2d(dst + bx * box_bytes, &tmR, bar, 32 * bx, row0 + r0);
+    } else {
+      for (int bx = 0; bx < nbox; ++bx)
+        for (int t = 0; t < (nr8 >> 3); ++t)
+          tma_load_2d(dst + bx * box_bytes + t * 1024, &tm8, bar, 32 * bx, row0 + r0 + 8 * t);
+    }
+  };
+  // statistics pass: plain row tiles of W, S (, W_snap): one 1-D bulk copy per array
+  auto issue_rows = [&](int j, int narr, int depth, int tr, int slot_b) {
     const int r0 = j * tr;
     if (r0 >= rows || lane != 0) return;
     const int st = j % depth;
     const int nr = min(tr, rows - r0);
-    const uint32_t bytes = (uint32_t)nr * ldw * 4u;       // rows are contiguous: ONE bulk copy per array
+    const uint32_t bytes = (uint32_t)nr * ldw * 4u;
     uint64_t* bar = &bars[st];
     mbar_expect_tx(bar, bytes * narr);
     unsigned char* dst = smem + (size_t)st * narr * slot_b;
@@ -228,78 +209,59 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   };
 
   // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
-  if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);     // start streaming W while the minibatch is gathered
+  if (warp == 0 && !(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
   for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
-  int exact_pred = 1, exact_pred2 = 1;
-  for (int e = tid; e < p.rows_alloc * MB; e += NT) {
-    int b = e / p.rows_alloc, r = e % p.rows_alloc;
+  for (int e = tid; e < p.rows_alloc * BTS; e += NT) {
+    const int b = e / p.rows_alloc, r = e - b * p.rows_alloc;
     float x = 0.f;
     if (b < B && r < rows) {
-      long long dr = p.idx ? p.idx[b] : b;
+      const long long dr = p.idx ? p.idx[b] : b;
       x = p.data[dr * p.ld_data + row0 + r];
     }
-    const float xr = p.pcd ? roundf(x) : 0.f;     // src/rbm.py:428; the nv slab is free until the last Gibbs step
     v0s[r * BTS + b] = x;
-    nvs[r * BTS + b] = xr;
-    exact_pred &= ((__float_as_uint(x) & 0x1FFFu) == 0u) ? 1 : 0;       // representable in tf32?
-    exact_pred2 &= ((__float_as_uint(xr) & 0x1FFFu) == 0u) ? 1 : 0;
+    nvs[r * BTS + b] = p.pcd ? roundf(x) : 0.f;   // src/rbm.py:428; the nv slab is free until the last Gibbs step
   }
-  const bool v0_exact = __syncthreads_and(exact_pred) != 0;    // binary / small-integer data: no low term
-  const bool x_exact = __syncthreads_and(exact_pred2) != 0;
+  __syncthreads();
   mark();   // gather done
 
-  // ---- propup of one staged tile on the tensor cores ------------------------------------
-  // out[b, j] += sum_i src[i][b] * W[i][j]; warp w owns the 8-column n-tiles w, w+8, ...;
-  // DUAL shares the W fragments with a second input slab.
-  auto up_mma = [&](const float* __restrict__ tile, const float* __restrict__ src, const float* __restrict__ src2,
-                    int nr8, float (&acc)[MT][NPW][4], float (&acc2)[MT][NPW][4], bool dual, bool a_exact,
-                    bool a2_exact) {
-    for (int i0 = 0; i0 < nr8; i0 += 8) {
-      uint32_t ah[MT][4], al[MT][4], a2h[MT][4], a2l[MT][4];
+  // ---- propup of one staged tile: acc[b] += src[r][b] * W[r, 4q..4q+3]; DUAL shares the W loads ----
+  auto up_tile = [&](const unsigned char* __restrict__ tile, const float* __restrict__ src,
+                     const float* __restrict__ src2, int nr, float4 (&acc)[BT], float4 (&acc2)[BT], bool dual) {
+    if (!col_ok) return;
+    const unsigned char* bp = tile + (q >> 3) * box_bytes;
+    const int c = q & 7;
+    for (int r = g; r < nr; r += p.G) {
+      const float4 w = *reinterpret_cast<const float4*>(bp + r * 128 + ((c ^ (r & 7)) << 4));
+      const float4* vr = reinterpret_cast<const float4*>(src + r * BTS);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const float* s0 = src + (i0 + lr) * BTS + mt * 16 + lq;
-        split_tf32(s0[0], ah[mt][0], al[mt][0]);
-        split_tf32(s0[8], ah[mt][1], al[mt][1]);
-        split_tf32(s0[4 * BTS], ah[mt][2], al[mt][2]);
-        split_tf32(s0[4 * BTS + 8], ah[mt][3], al[mt][3]);
-        if (dual) {
-          const float* t0 = src2 + (i0 + lr) * BTS + mt * 16 + lq;
-          split_tf32(t0[0], a2h[mt][0], a2l[mt][0]);
-          split_tf32(t0[8], a2h[mt][1], a2l[mt][1]);
-          split_tf32(t0[4 * BTS], a2h[mt][2], a2l[mt][2]);
-          split_tf32(t0[4 * BTS + 8], a2h[mt][3], a2l[mt][3]);
+      for (int b4 = 0; b4 < BTP / 4; ++b4) {
+        const float4 vv = vr[b4];
+        const float xs[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int b = b4 * 4 + t;
+          if (b < BT) {
+            acc[b].x = fmaf(xs[t], w.x, acc[b].x);
+            acc[b].y = fmaf(xs[t], w.y, acc[b].y);
+            acc[b].z = fmaf(xs[t], w.z, acc[b].z);
+            acc[b].w = fmaf(xs[t], w.w, acc[b].w);
+          }
         }
       }
-      // B fragments of all n-tiles first, then the three split terms term-major so that
-      // back-to-back MMAs never hit the same accumulator (dependent-issue latency)
-      uint32_t bh[NPW][2], bl[NPW][2];
+      if (dual) {
+        const float4* xr = reinterpret_cast<const float4*>(src2 + r * BTS);
 #pragma unroll
-      for (int nt = 0; nt < NPW; ++nt) {
-        const int n0 = (warp + nt * NWARP) * 8;
-        if (n0 < ncols8) {
-          const float* w0 = tile + (i0 + lr) * ldp + n0 + lq;
-          split_tf32(w0[0], bh[nt][0], bl[nt][0]);
-          split_tf32(w0[4 * ldp], bh[nt][1], bl[nt][1]);
-        }
-      }
+        for (int b4 = 0; b4 < BTP / 4; ++b4) {
+          const float4 vv = xr[b4];
+          const float xs[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        if (term == 2 && a_exact && (!dual || a2_exact)) continue;   // no low parts (binary / integer inputs)
-#pragma unroll
-        for (int nt = 0; nt < NPW; ++nt) {
-          const int n0 = (warp + nt * NWARP) * 8;
-          if (n0 < ncols8) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              if (term == 0) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
-              else if (term == 1) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
-              else if (!a_exact) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
-              if (dual) {     // second input: round(v0) is integer-valued -> exact in tf32, no low term
-                if (term == 0) mma_tf32(acc2[mt][nt], a2h[mt], bh[nt][0], bh[nt][1]);
-                else if (term == 1) mma_tf32(acc2[mt][nt], a2h[mt], bl[nt][0], bl[nt][1]);
-                else if (!a2_exact) mma_tf32(acc2[mt][nt], a2l[mt], bh[nt][0], bh[nt][1]);
-              }
+          for (int t = 0; t < 4; ++t) {
+            const int b = b4 * 4 + t;
+            if (b < BT) {
+              acc2[b].x = fmaf(xs[t], w.x, acc2[b].x);
+              acc2[b].y = fmaf(xs[t], w.y, acc2[b].y);
+              acc2[b].z = fmaf(xs[t], w.z, acc2[b].z);
+              acc2[b].w = fmaf(xs[t], w.w, acc2[b].w);
             }
           }
         }
@@ -307,23 +269,34 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     }
   };
 
-  // ---- this CTA's partial [BT][ldw] straight from the accumulator fragments to global scratch ----
-  auto flush_partial = [&](float (&acc)[MT][NPW][4], int set) {
-    if (rows <= 0) return;
-    float* dst = p.part + ((size_t)cta * 2 + set) * BT * ldw;
+  // ---- CTA partial [BT][ldw]: sum over the G row groups (fixed order), then to global scratch ---
+  // uses hs as the staging accumulator (it is reloaded after the reduction anyway)
+  auto flush_partial = [&](float4 (&acc)[BT], int set) {
+    float4* stage = reinterpret_cast<float4*>(hs);
+    const int ldh4 = ldh >> 2;
+    for (int gg = 0; gg < p.G; ++gg) {
+      if (col_ok && g == gg) {
 #pragma unroll
-    for (int nt = 0; nt < NPW; ++nt) {
-      const int j = (warp + nt * NWARP) * 8 + 2 * lr;
-      if (j < ldw) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int b = mt * 16 + lq;
-          if (b < BT) __stcg(reinterpret_cast<float2*>(dst + b * ldw + j), make_float2(acc[mt][nt][0], acc[mt][nt][1]));
-          if (b + 8 < BT)
-            __stcg(reinterpret_cast<float2*>(dst + (b + 8) * ldw + j), make_float2(acc[mt][nt][2], acc[mt][nt][3]));
+        for (int b = 0; b < BT; ++b) {
+          float4 a = acc[b];
+          if (gg > 0) {
+            const float4 o = stage[b * ldh4 + q];
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          }
+          stage[b * ldh4 + q] = a;
         }
       }
+      __syncthreads();
     }
+    if (rows > 0) {
+      float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)cta * 2 + set) * BT * ldw);
+      const int ldw4 = ldw >> 2;
+      for (int e = tid; e < BT * p.CQ; e += NT) {
+        const int b = e / p.CQ, qq = e - b * p.CQ;
+        __stcg(&dst[b * ldw4 + qq], stage[b * ldh4 + qq]);
+      }
+    }
+    __syncthreads();
   };
 
   // ---- distributed reduction of the hidden pre-activations + epilogue ----------------
@@ -378,10 +351,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     }
   };
 
+  // chain state [BT][ldw] from L2 into the shared-memory panel (float4, four loads in flight per thread)
   auto load_hs = [&](const float* src, int ld_src, int nrows_src) {
-    // [BT][ldw] chain state from L2 into the padded shared-memory panel.  float4 loads, four
-    // independent loads in flight per thread (a dependent chain of L2 round trips was 3-7 us here).
-    int pred = 1;
     const int ldw4 = ldw >> 2, n4 = BT * ldw4;
     const bool vec = (ld_src & 3) == 0 && (((uintptr_t)src) & 15) == 0;
     for (int e0 = tid; e0 < n4; e0 += 4 * NT) {
@@ -410,37 +381,30 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         if (e < n4) {
           const int b = e / ldw4, j = (e - b * ldw4) * 4;
           *reinterpret_cast<float4*>(hs + b * ldh + j) = x[u];
-          pred &= (((__float_as_uint(x[u].x) | __float_as_uint(x[u].y) | __float_as_uint(x[u].z) |
-                     __float_as_uint(x[u].w)) & 0x1FFFu) == 0u) ? 1 : 0;
         }
       }
     }
-    return __syncthreads_and(pred) != 0;      // {0,1} chain states are exact in tf32
+    __syncthreads();
   };
 
   // =============================== pass 0: positive phase ===============================
   {
     const int depth = p.nslots;
-    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth, p.TR, p.slot_bytes);
-    float acc[MT][NPW][4], acc2[MT][NPW][4];
+    if (warp == 0 && !(F & 2)) for (int j = 1; j < depth; ++j) issue(j, depth);
+    float4 acc[BT], acc2[BT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NPW; ++nt)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[mt][nt][c] = acc2[mt][nt][c] = 0.f;
+    for (int b = 0; b < BT; ++b) acc[b] = acc2[b] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
-      wait_stage(st);
-      const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
-      const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7;
-      up_mma(tile, v0s + (size_t)j * p.TR * BTS, nvs + (size_t)j * p.TR * BTS, nr8, acc, acc2, ALLOW_DUAL && p.pcd != 0, v0_exact,
-             x_exact);
+      if (!(F & 2)) wait_stage(st);
+      const unsigned char* tile = smem + (size_t)st * p.slot_bytes;
+      const int nr = min(R, rows - j * R);
+      if (!(F & 1)) up_tile(tile, v0s + (size_t)j * R * BTS, nvs + (size_t)j * R * BTS, nr, acc, acc2, p.pcd != 0);
       __syncthreads();
-      if (warp == 0) issue(j + depth, 1, depth, p.TR, p.slot_bytes);
+      if (warp == 0 && !(F & 2)) issue(j + depth, depth);
     }
     mark();   // pass-0 tiles done
     flush_partial(acc, 0);
-    if (ALLOW_DUAL && p.pcd) flush_partial(acc2, 1);
+    if (p.pcd) flush_partial(acc2, 1);
   }
   mark();
   grid_sync(p.bar, bar_target);
@@ -449,39 +413,34 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   reduce_hidden(p.pcd ? 2 : 1, p.PH, seg(0, 0), !p.pcd, false);
   mark();   // reduce 0 done
   grid_sync(p.bar, bar_target);
-  if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);     // W is unchanged until the update: prefetch the next pass now
-  bool h_exact = p.pcd ? load_hs(p.P, H, B) : load_hs(p.HS, ldw, BT);
+  if (warp == 0 && !(F & 32)) issue(0, p.nslots);     // W is unchanged until the update: prefetch the next pass now
+  if (p.pcd) load_hs(p.P, H, B); else load_hs(p.HS, ldw, BT);
   mark();
 
-  // pseudo-likelihood monitor (src/rbm.py:421-447) — CTA 0, uses the pre-update W, hb, vb
-  if (p.pcd && cta == 0) {
+  // pseudo-likelihood monitor (src/rbm.py:421-447), pre-update W, hb, vb: one minibatch row per CTA, taken
+  // from the END of the grid (the last CTA owns the fewest rows); its loads overlap the tile prefetch above
+  if (p.pcd) {
     const int bit = *p.bit_idx;
-    for (int b = warp; b < B; b += NWARP) {
-      long long dr = p.idx ? p.idx[b] : b;
-      float x = roundf(p.data[dr * p.ld_data + bit]);
-      float d = 1.f - 2.f * x;
+    for (int b = (int)gridDim.x - 1 - cta; b < B; b += gridDim.x) {
+      const long long dr = p.idx ? p.idx[b] : b;
+      const float x = roundf(p.data[dr * p.ld_data + bit]);
+      const float d = 1.f - 2.f * x;
       float h0 = 0.f, h1 = 0.f;
-      for (int j = lane; j < H; j += 32) {
-        float pre = __ldcg(&p.PREX[b * ldw + j]);
+      for (int j = tid; j < H; j += NT) {
+        const float pre = __ldcg(&p.PREX[b * ldw + j]);
         h0 += softplusf_(pre);
         h1 += softplusf_(pre + d * p.W[(size_t)bit * ldw + j]);
       }
-      h0 = warp_sum(h0);
-      h1 = warp_sum(h1);
-      if (lane == 0) {
-        float vbv = p.vb[bit], vterm;
-        if (p.kind == MDBN_GRBM) { float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
+      h0 = block_sum(h0, misc);
+      h1 = block_sum(h1, misc);
+      if (tid == 0) {
+        const float vbv = p.vb[bit];
+        float vterm;
+        if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
         else vterm = d * vbv;
-        misc[32 + b] = -(float)V * softplusf_((h1 - h0) + vterm);
+        __stcg(&p.cost_part[b], -(float)V * softplusf_((h1 - h0) + vterm));
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f;
-      for (int b = 0; b < B; ++b) s += misc[32 + b];
-      misc[63] = s * p.cost_scale;
-    }
-    __syncthreads();
   }
 
   // =============================== passes 1..k: fused Gibbs steps ===============================
@@ -492,132 +451,74 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s);
     const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s);
     const int depth = p.nslots;
-    if (warp == 0) for (int j = 1; j < depth; ++j) issue(j, 1, depth, p.TR, p.slot_bytes);   // job 0 was prefetched
-    float acc[MT][NPW][4];
+    if (warp == 0 && !(F & 32)) for (int j = 1; j < depth; ++j) issue(j, depth);   // job 0 was prefetched
+    float4 acc[BT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NPW; ++nt)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+    for (int b = 0; b < BT; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
-      if (j < 3) mark2();
-      wait_stage(st);
-      if (j < 3) mark2();
-      const float* tile = reinterpret_cast<const float*>(smem + (size_t)st * p.slot_bytes);
-      const int nr = min(p.TR, rows - j * p.TR), nr8 = (nr + 7) & ~7, ntd = nr8 >> 3;
-      // ---- propdown of the tile rows: out[b, i] = sum_j h[b][j] W[i][j]; the 8 warps split j ----
-      // mma.sync has a long dependent-issue latency on sm_100: every split term (and, for one
-      // m-tile, every other k-step) gets its own accumulator so ~3*KI*ntd MMAs are in flight
-      {
-        constexpr int KI = MT == 1 ? 2 : 1;
-        float dacc[KI][3][MT][NTD][4];
+      if (!(F & 32)) wait_stage(st);
+      const unsigned char* tile = smem + (size_t)st * p.slot_bytes;
+      const int nr = min(R, rows - j * R);
+      // ---- propdown of the tile rows, lane = row: out[b] = sum_j h[b][j] W[row][j] stays in one thread;
+      //      the warps (and, for short tiles, the lane groups) split the boxes of 32 columns ----
+      if (!(F & 4)) {
+        float dacc[BT];
 #pragma unroll
-        for (int ki = 0; ki < KI; ++ki)
+        for (int b = 0; b < BT; ++b) dacc[b] = 0.f;
+        for (int bx = warp * SUBS + dsub; bx < nbox; bx += NWARP * SUBS) {
+          const unsigned char* bp = tile + bx * box_bytes + drow * 128;
+          const float* hb0 = hs + bx * 32;
 #pragma unroll
-          for (int t3 = 0; t3 < 3; ++t3)
+          for (int c = 0; c < 8; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(bp + ((c ^ (drow & 7)) << 4));
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < NTD; ++nt)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) dacc[ki][t3][mt][nt][c] = 0.f;
-        for (int jb = warp * 8; jb < ncols8; jb += NWARP * 8 * KI) {
-#pragma unroll
-          for (int ki = 0; ki < KI; ++ki) {
-            const int j0 = jb + ki * NWARP * 8;
-            if (j0 < ncols8) {
-              uint32_t ah[MT][4], al[MT][4];
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const float* h0 = hs + (mt * 16 + lq) * ldh + j0 + lr;
-                split_tf32(h0[0], ah[mt][0], al[mt][0]);
-                split_tf32(h0[8 * ldh], ah[mt][1], al[mt][1]);
-                split_tf32(h0[4], ah[mt][2], al[mt][2]);
-                split_tf32(h0[8 * ldh + 4], ah[mt][3], al[mt][3]);
-              }
-#pragma unroll
-              for (int nt = 0; nt < NTD; ++nt) {
-                if (nt < ntd) {
-                  const float* w0 = tile + (nt * 8 + lq) * ldp + j0 + lr;
-                  uint32_t bh0, bl0, bh1, bl1;
-                  split_tf32(w0[0], bh0, bl0);
-                  split_tf32(w0[4], bh1, bl1);
-#pragma unroll
-                  for (int mt = 0; mt < MT; ++mt) {
-                    mma_tf32(dacc[ki][0][mt][nt], ah[mt], bh0, bh1);
-                    mma_tf32(dacc[ki][1][mt][nt], ah[mt], bl0, bl1);
-                    if (!h_exact) mma_tf32(dacc[ki][2][mt][nt], al[mt], bh0, bh1);
-                  }
-                }
-              }
+            for (int b = 0; b < BT; ++b) {
+              const float4 h4 = *reinterpret_cast<const float4*>(hb0 + b * ldh + c * 4);     // warp-broadcast
+              dacc[b] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, dacc[b]))));
             }
           }
         }
+        float* d0 = dred + (size_t)(warp * SUBS + dsub) * BT * R + drow;
 #pragma unroll
-        for (int nt = 0; nt < NTD; ++nt) {
-          if (nt < ntd) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              float r4[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float small = dacc[0][1][mt][nt][c] + dacc[0][2][mt][nt][c];
-                float big = dacc[0][0][mt][nt][c];
-                if (KI == 2) {
-                  small += dacc[KI - 1][1][mt][nt][c] + dacc[KI - 1][2][mt][nt][c];
-                  big += dacc[KI - 1][0][mt][nt][c];
-                }
-                r4[c] = big + small;
-              }
-              float* d0 = dred + ((size_t)warp * MB + mt * 16 + lq) * p.TR + nt * 8 + 2 * lr;
-              *reinterpret_cast<float2*>(d0) = make_float2(r4[0], r4[1]);
-              *reinterpret_cast<float2*>(d0 + 8 * p.TR) = make_float2(r4[2], r4[3]);
-            }
-          }
-        }
+        for (int b = 0; b < BT; ++b) d0[b * R] = dacc[b];
       }
-      if (j < 3) mark2();
       __syncthreads();
-      if (j < 3) mark2();
       // ---- visible epilogue: bias, activation, sampling (src/rbm.py:226-240 / :650-660) ----
-      for (int it = tid; it < nr8 * MB; it += NT) {
-        const int r = it / MB, b = it % MB;
+      for (int it = tid; it < nr * BTS && !(F & 8); it += NT) {
+        const int r = it / BTS, b = it - r * BTS;
         float vin = 0.f, mean = 0.f;
-        if (r < nr && b < B) {
+        if (b < B) {
           float sum = 0.f;
-#pragma unroll
-          for (int w2 = 0; w2 < NWARP; ++w2) sum += dred[((size_t)w2 * MB + b) * p.TR + r];
-          const int gi = row0 + j * p.TR + r;
-          const float pre = sum + vbs[j * p.TR + r];
+          for (int w2 = 0; w2 < NWARP * SUBS; ++w2) sum += dred[((size_t)w2 * BT + b) * R + r];
+          const int lr_ = j * R + r;
+          const float pre = sum + vbs[lr_];
           if (p.kind == MDBN_GRBM) {
             mean = pre;
             vin = pre;        // mean-field visible: h given v_MEAN (src/rbm.py:669)
           } else {
             mean = sigmoidf_(pre);
-            vin = rng_uniform(rs_v, (long long)b * V + gi) < mean ? 1.f : 0.f;
+            vin = rng_uniform(rs_v, (long long)b * V + row0 + lr_) < mean ? 1.f : 0.f;
           }
           if (last && !p.pcd) {
-            const float t = v0s[(j * p.TR + r) * BTS + b];
-            if (p.kind == MDBN_GRBM) { float d = sigmoidf_(pre) - t; cost_acc += d * d; }   // :697
-            else cost_acc += t * softplusf_(-pre) + (1.f - t) * softplusf_(pre);          // :479-480
+            const float t = v0s[lr_ * BTS + b];
+            if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t; cost_acc += d * d; }   // :697
+            else cost_acc += t * softplusf_(-pre) + (1.f - t) * softplusf_(pre);                  // :479-480
           }
         }
         vt[r * BTS + b] = vin;
-        if (last) nvs[(j * p.TR + r) * BTS + b] = mean;
+        if (last) nvs[(j * R + r) * BTS + b] = mean;
       }
       __syncthreads();
-      if (j < 3) mark2();
       // ---- propup accumulation from the same tile ----
-      up_mma(tile, vt, vt, nr8, acc, acc, false, p.kind == MDBN_RBM, true);
+      if (!(F & 16)) up_tile(tile, vt, vt, nr, acc, acc, false);
       __syncthreads();
-      if (warp == 0) issue(j + depth, 1, depth, p.TR, p.slot_bytes);
+      if (warp == 0 && !(F & 32)) issue(j + depth, depth);
     }
     if (last) mark();   // Gibbs tiles done
     flush_partial(acc, 0);
     if (last && !p.pcd) {
-      float c = block_sum(cost_acc, misc);
+      const float c = block_sum(cost_acc, misc);
       if (tid == 0) __stcg(&p.cost_part[cta], c);
     }
     grid_sync(p.bar, bar_target);
@@ -626,8 +527,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     grid_sync(p.bar, bar_target);
     if (last) mark();
     if (!last) {
-      if (warp == 0) issue(0, 1, p.nslots, p.TR, p.slot_bytes);
-      h_exact = load_hs(p.HS, ldw, BT);
+      if (warp == 0 && !(F & 32)) issue(0, p.nslots);
+      load_hs(p.HS, ldw, BT);
     }
   }
 
@@ -635,12 +536,12 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   {
     // short tiles (8 rows) for this pass: it streams 2-3 arrays and wants a deep pipeline
     const int narr = p.wc != 0.f ? 3 : 2;
-    const int TRS = 8, slot_s = (TRS * ldp * 4 + 127) & ~127;
+    const int TRS = 8, slot_s = (TRS * ldw * 4 + 127) & ~127;
     int depth = (p.nslots * p.slot_bytes) / (narr * slot_s);
     depth = depth > MAX_SLOTS ? MAX_SLOTS : depth;
     const int ntiles_s = (rows + TRS - 1) / TRS;
-    if (warp == 0) for (int j = 0; j < depth; ++j) issue(j, narr, depth, TRS, slot_s);
-    const int ldw4 = ldw >> 2;
+    if (warp == 0) for (int j = 0; j < depth; ++j) issue_rows(j, narr, depth, TRS, slot_s);
+    const int ldw4 = ldw >> 2, ldw4x = ldw >> 2;
     float4 ph[BT], nh[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
@@ -662,7 +563,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
       if (col_ok) {
         for (int r = g; r < nr; r += p.G) {
           const int lr_ = j * TRS + r;
-          float4 w = wt[r * ldp4 + q], sp = st[r * ldp4 + q];
+          float4 w = wt[r * ldw4x + q], sp = st[r * ldw4x + q];
           const float4* a4 = reinterpret_cast<const float4*>(v0s + lr_ * BTS);
           const float4* n4 = reinterpret_cast<const float4*>(nvs + lr_ * BTS);
           float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -683,7 +584,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
           }
           float wv[4] = {w.x, w.y, w.z, w.w}, sv[4] = {sp.x, sp.y, sp.z, sp.w}, gv[4] = {gs.x, gs.y, gs.z, gs.w};
           float snv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (narr > 2) { float4 t4 = sn[r * ldp4 + q]; snv[0] = t4.x; snv[1] = t4.y; snv[2] = t4.z; snv[3] = t4.w; }
+          if (narr > 2) { float4 t4 = sn[r * ldw4x + q]; snv[0] = t4.x; snv[1] = t4.y; snv[2] = t4.z; snv[3] = t4.w; }
           float wo[4], so[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -710,7 +611,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
         }
       }
       __syncthreads();
-      if (warp == 0) issue(j + depth, narr, depth, TRS, slot_s);
+      if (warp == 0) issue_rows(j + depth, narr, depth, TRS, slot_s);
     }
     // visible bias (rows owned by this CTA)  src/rbm.py:417
     for (int r = tid; r < rows; r += NT) {
@@ -733,7 +634,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
     if (cta == 0 && tid == 0) {
       float c;
       if (p.pcd) {
-        c = misc[63];
+        c = 0.f;
+        for (int b = 0; b < B; ++b) c += __ldcg(&p.cost_part[b]);
+        c *= p.cost_scale;
         *p.bit_idx = (*p.bit_idx + 1) % V;                                 // :445
       } else {
         c = 0.f;
@@ -749,7 +652,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    unsigned long long prev = atomicAdd(p.bar + 1, 1ULL);
+    const unsigned long long prev = atomicAdd(p.bar + 1, 1ULL);
     if (prev == gridDim.x - 1) {
       p.bar[0] = 0ULL;
       p.bar[1] = 0ULL;
@@ -758,63 +661,75 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* tm, const float* W, int V, int ldw, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)ldw, (cuuint64_t)V};
+  cuuint64_t strides[1] = {(cuuint64_t)ldw * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MDBN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
 struct Geometry {
-  int BT, NPW, NT, rows_per_cta, rows_alloc, n_active, CQ, GW, G, TR, nslots, grid, ldp, ldh, slot_bytes;
+  int BT, rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, grid, ldh, slot_bytes, ring_bytes;
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
   size_t smem;
   bool ok;
 };
 
-static int pad_mod32(int n, int want) { return n + ((want - n % 32) + 32) % 32; }
-
 static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   Geometry g{};
   g.ok = false;
   g.BT = a.B <= 10 ? 10 : (a.B <= 20 ? 20 : 0);
-  if (!g.BT || a.ldw % 4 != 0) return g;
+  if (!g.BT || a.ldw % 4 != 0 || !get_encode()) return g;
   if (((uintptr_t)a.W | (uintptr_t)a.W_speed | (uintptr_t)a.W_snap) & 15) return g;
-  const int MT = g.BT > 16 ? 2 : 1, MB = 16 * MT, BTS = MT == 1 ? 24 : 40;
-  const bool pcd = a.persistent != nullptr;
+  const int BTS = (g.BT + 3) / 4 * 4;
   g.CQ = a.ldw / 4;
-  const int ncols8 = (a.H + 7) & ~7;
-  if (ncols8 > 1024) return g;
-  // 512 threads (16 warps) was measured slower (Gibbs pass 40 vs 31 us): register spills at 128 regs/thread
-  g.NT = 256;
-  if (g.CQ > g.NT) return g;
-  const bool wide = ncols8 > 512;
-  g.NPW = (g.NT == 512) ? (wide ? 8 : 4) : (wide ? 16 : 8);
-  if (wide && MT == 2 && pcd) return g;     // register budget of the dual accumulators
+  if (g.CQ > NT) return g;
   if (g.CQ <= 32) { g.GW = 1; while (g.GW < g.CQ) g.GW <<= 1; } else g.GW = (g.CQ + 31) / 32 * 32;
-  g.G = g.NT / g.GW;
+  g.G = NT / g.GW;
   g.grid = c->num_sms;
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
   g.rows_alloc = (g.rows_per_cta + 7) & ~7;
   g.n_active = (a.V + g.rows_per_cta - 1) / g.rows_per_cta;
-  if (a.ldw != ncols8) return g;      // rows padded to 8 floats (the Python host allocates W that way)
-  g.ldp = a.ldw;                      // staged rows keep the global stride: one bulk copy per tile
-
-  g.ldh = pad_mod32(ncols8, 20);
-  int tr = (40 * 1024) / (g.ldp * 4);
-  tr &= ~7;
-  if (tr < 8) return g;
-  if (tr > MAX_TR) tr = MAX_TR;
-  if (wide && tr > 16) tr = 16;
-  // no point in tiles taller than the slab
-  while (tr > 8 && tr - 8 >= g.rows_alloc) tr -= 8;
-  g.TR = tr;
-  g.slot_bytes = (g.TR * g.ldp * 4 + 127) & ~127;
+  g.nbox = (a.ldw + 31) / 32;
+  g.ldh = g.nbox * 32;
+  // stage = R rows x all columns as nbox swizzled boxes, at most 56 KB
+  g.R = 32;
+  while (g.R > 8 && (g.nbox * g.R * 128 > 56 * 1024 || g.R / 2 >= g.rows_alloc)) g.R >>= 1;
+  if (g.nbox * g.R * 128 > 64 * 1024) return g;
+  g.slot_bytes = g.nbox * g.R * 128;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
-  const size_t hs_b = up128((size_t)MB * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
-               vt_b = up128((size_t)MAX_TR * BTS * 4), dred_b = up128((size_t)(g.NT / 32) * MB * g.TR * 4);
-  const size_t vb_b = up128((size_t)g.rows_alloc * 4);
+  const size_t hs_b = up128((size_t)g.BT * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
+               vt_b = up128((size_t)32 * BTS * 4), dred_b = up128((size_t)NWARP * 32 * g.BT * 4),
+               vb_b = up128((size_t)g.rows_alloc * 4);
   const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256 + vb_b;
   const size_t smem_max = 227 * 1024;
-  const int narr = a.weightcost != 0.f ? 3 : 2;
-  if (fixed + (size_t)narr * g.slot_bytes > smem_max) return g;
+  if (fixed + 2 * (size_t)g.slot_bytes > smem_max) return g;
   g.nslots = (int)((smem_max - fixed) / g.slot_bytes);
   if (g.nslots > MAX_SLOTS) g.nslots = MAX_SLOTS;
-  if (g.nslots < narr || g.nslots < 2) return g;
-  size_t off = (size_t)g.nslots * g.slot_bytes;
+  g.ring_bytes = g.nslots * g.slot_bytes;
+  const int narr = a.weightcost != 0.f ? 3 : 2;
+  if ((size_t)narr * ((8 * a.ldw * 4 + 127) & ~127) > (size_t)g.ring_bytes) return g;
+  size_t off = (size_t)g.ring_bytes;
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return (int)o; };
   g.off_hs = take(hs_b);
   g.off_v0 = take(slab_b);
@@ -829,15 +744,15 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   return g;
 }
 
-template <int BT, int NPW, int NT>
-static int launch(mdbn_ctx* c, const Params& p, const Geometry& g, cudaStream_t st) {
+template <int BT>
+static int launch(mdbn_ctx* c, const CUtensorMap* tms, const Params& p, const Geometry& g, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kfn = cd_skinny_kernel<BT, NPW, NT>;
+  auto kfn = cd_skinny_kernel<BT>;
   if (!configured[c->device]) {
     MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[c->device] = true;
   }
-  void* args[] = {(void*)&p};
+  void* args[] = {(void*)&tms[0], (void*)&tms[1], (void*)&p};
   MDBN_CUDA(cudaLaunchCooperativeKernel((void*)kfn, dim3(g.grid), dim3(NT), args, g.smem, st));
   c->launches++;
   return 0;
@@ -873,8 +788,8 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
   p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.n_active = g.n_active;
-  p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.TR = g.TR; p.nslots = g.nslots;
-  p.ldp = g.ldp; p.ldh = g.ldh; p.slot_bytes = g.slot_bytes;
+  p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.R = g.R; p.nbox = g.nbox; p.nslots = g.nslots;
+  p.ldh = g.ldh; p.slot_bytes = g.slot_bytes; p.ring_bytes = g.ring_bytes;
   p.off_hs = g.off_hs; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vt = g.off_vt; p.off_dred = g.off_dred;
   p.off_bars = g.off_bars; p.off_misc = g.off_misc; p.off_vb = g.off_vb;
 
@@ -888,10 +803,9 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   const size_t before_n = wb.n;
   float* base = (float*)ws_get(c, WS_SKINNY, total_f * sizeof(float));
   if (!base) return 3;
-  // layout depends on (BT, ldw, n_active): re-zero when the allocation or the layout key changes
   static thread_local unsigned long long last_key = 0;
-  unsigned long long key = ((unsigned long long)g.BT << 48) ^ ((unsigned long long)a.ldw << 24) ^
-                           (unsigned long long)g.n_active ^ ((unsigned long long)(uintptr_t)base << 1);
+  const unsigned long long key = ((unsigned long long)g.BT << 48) ^ ((unsigned long long)a.ldw << 24) ^
+                                 (unsigned long long)g.n_active ^ ((unsigned long long)(uintptr_t)base << 1);
   if (before != wb.p || before_n != wb.n || key != last_key) {
     MDBN_CUDA(cudaMemsetAsync(base, 0, wb.n, st));
     last_key = key;
@@ -904,21 +818,22 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.cost_part = p.PREX + hb_f;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
-  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;   // needs 32 slots
+  static const int dbg_flags = getenv("MDBN_SKINNY_DEBUG") ? atoi(getenv("MDBN_SKINNY_DEBUG")) : 0;
+  p.dbg_flags = dbg_flags;
+  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 8 : nullptr;
+  CUtensorMap tms[2];
+  MDBN_TRY(sk::make_map(&tms[0], a.W, a.V, a.ldw, g.R));
+  MDBN_TRY(sk::make_map(&tms[1], a.W, a.V, a.ldw, 8));
   int rc = 2;
-  if (g.BT == 10 && g.NPW == 8) rc = sk::launch<10, 8, 256>(c, p, g, st);
-  else if (g.BT == 10 && g.NPW == 16) rc = sk::launch<10, 16, 256>(c, p, g, st);
-  else if (g.BT == 20 && g.NPW == 8) rc = sk::launch<20, 8, 256>(c, p, g, st);
-  else if (g.BT == 20 && g.NPW == 16) rc = sk::launch<20, 16, 256>(c, p, g, st);
-  else set_error("skinny path: no kernel for BT=%d NPW=%d", g.BT, g.NPW);
+  if (g.BT == 10) rc = sk::launch<10>(c, tms, p, g, st);
+  else if (g.BT == 20) rc = sk::launch<20>(c, tms, p, g, st);
+  else set_error("skinny path: no kernel for BT=%d", g.BT);
   if (rc == 0 && p.dbg) {
-    unsigned long long t[32];
+    unsigned long long t[16];
     MDBN_CUDA(cudaStreamSynchronize(st));
     MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[skinny timeline us] V=%d H=%d B=%d k=%d:", a.V, a.H, a.B, a.k);
+    fprintf(stderr, "[skinny timeline us] V=%d H=%d B=%d k=%d R=%d nslots=%d:", a.V, a.H, a.B, a.k, g.R, g.nslots);
     for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
-    fprintf(stderr, "\n   gibbs tiles (wait< wait> D sync epi | ...):");
-    for (int i = 16; i < 31; ++i) fprintf(stderr, " %.2f", (double)(t[i] - t[0]) * 1e-3);
     fprintf(stderr, "\n");
   }
   return rc;
