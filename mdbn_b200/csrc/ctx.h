@@ -16,6 +16,8 @@ struct mdbn_ctx {
   Buf ws[16];
   unsigned int* barrier = nullptr;   // grid barrier word for the persistent kernel
   int tf32_phases = 0;               // single-phase calls use the tcgen05 TF32 path (mdbn_set_tf32_phases)
+  unsigned skinny_parity = 0;        // which of the two accumulator sets the next skinny launch uses
+  unsigned long long skinny_key = 0; // layout of the accumulator scratch (re-zeroed when it changes)
 };
 
 namespace mdbn {

@@ -52,15 +52,18 @@ struct Params {
   long long u_step_stride, u_off_v, u_off_h;
   // geometry
   int rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, ldh, slot_bytes, ring_bytes;
-  // global scratch
-  float* part;        // [n_active][2][BT][ldw]
-  float *PH, *NH, *HS, *PREX;   // [BT][ldw], zero-initialised, padded columns never written
-  float* cost_part;   // [gridDim]
+  // global scratch: fixed-point (2^-32) accumulators of the hidden pre-activation sums, [5][BT][ldw]:
+  // 0 = positive phase, 1 = round(v0) (pseudo-likelihood), 2..4 = Gibbs steps (rotating).  Zero on entry;
+  // `acc_other` is the set of the previous launch, cleared by this one.
+  unsigned long long *acc, *acc_other;
+  int n_acc;          // BT * ldw
+  float* cost_part;   // [max(gridDim, BT)]
+  float* PHf;         // [BT][ldw] positive-phase hidden means as fp32 (written in slices after barrier 0)
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
   unsigned long long* dbg;   // optional phase timeline (MDBN_SKINNY_TIMING=1), CTA 0 only
   int dbg_flags;             // MDBN_SKINNY_DEBUG: skip parts of the passes (timing experiments only; results are wrong)
   // smem byte offsets
-  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
+  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb, off_hb;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +100,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Fixed-point image of a partial sum: integer additions commute, so the grid-wide sum built with
+// red.global.add.u64 is bitwise reproducible whatever order the CTAs arrive in.  2^-32 resolution, |x| < 2^31.
+__device__ __forceinline__ unsigned long long to_fixed(float x) {
+  return (unsigned long long)__float2ll_rn(x * 4294967296.0f);
+}
+__device__ __forceinline__ float from_fixed(long long s) { return __ll2float_rn(s) * 2.3283064365386963e-10f; }
+// sigmoid on the MUFU pipe (ex2.approx + rcp.approx, a few ulp): for the hidden layer rebuilt by every CTA
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast_(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
 // Device-wide barrier.  All CTAs are co-resident (cooperative launch).  The counter is
 // monotonic within a launch and reset by the last CTA to leave the kernel.
 __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long long& target) {
@@ -127,6 +147,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, pl cost
   float* vbs = reinterpret_cast<float*>(smem + p.off_vb);     // [rows_alloc] visible bias of the owned rows
+  float* hbs = reinterpret_cast<float*>(smem + p.off_hb);     // [ldh] hidden bias as it was on entry
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
@@ -159,10 +180,16 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int e = tid; e < BT * ldh; e += NT) hs[e] = 0.f;
+  for (int j = tid; j < ldh; j += NT) hbs[j] = j < H ? p.hb[j] : 0.f;
+  // clear the accumulator set of the previous launch (nobody touches it during this one)
+  for (int i = cta * NT + tid; i < 5 * p.n_acc; i += gridDim.x * NT) __stcg(&p.acc_other[i], 0ULL);
   __syncthreads();
 
   // ---- tile pipeline --------------------------------------------------------------
-  // W-only passes: stage j = rows [j*R, j*R+R) x all columns as nbox swizzled boxes (TMA).  lane 0 of warp 0.
+  // W-only passes: stage j = rows [j*R, j*R+R) x all columns as nbox swizzled boxes (TMA).  Called by ALL
+  // warps: lane 0 of warp w issues boxes w, w+NWARP, ... (one thread issuing a whole stage costs ~1 us per
+  // tile on the critical path); warp 0 also posts the byte count.  A complete_tx that overtakes the
+  // expect_tx is legal: the phase cannot complete before the arrival that carries the expect_tx.
   auto issue = [&](int j, int depth) {
     const int r0 = j * R;
     if (r0 >= rows || lane != 0) return;
@@ -170,11 +197,11 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     const int nr8 = (min(R, rows - r0) + 7) & ~7;
     uint64_t* bar = &bars[st];
     unsigned char* dst = smem + (size_t)st * p.slot_bytes;
-    mbar_expect_tx(bar, (uint32_t)nbox * nr8 * 128u);
+    if (warp == 0) mbar_expect_tx(bar, (uint32_t)nbox * nr8 * 128u);
     if (nr8 == R) {
-      for (int bx = 0; bx < nbox; ++bx) tma_load_2d(dst + bx * box_bytes, &tmR, bar, 32 * bx, row0 + r0);
+      for (int bx = warp; bx < nbox; bx += NWARP) tma_load_2d(dst + bx * box_bytes, &tmR, bar, 32 * bx, row0 + r0);
     } else {
-      for (int bx = 0; bx < nbox; ++bx)
+      for (int bx = warp; bx < nbox; bx += NWARP)
         for (int t = 0; t < (nr8 >> 3); ++t)
           tma_load_2d(dst + bx * box_bytes + t * 1024, &tm8, bar, 32 * bx, row0 + r0 + 8 * t);
     }
@@ -209,76 +236,111 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   };
 
   // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
-  if (warp == 0 && !(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
+  if (!(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
   for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
-  for (int e = tid; e < p.rows_alloc * BTS; e += NT) {
-    const int b = e / p.rows_alloc, r = e - b * p.rows_alloc;
-    float x = 0.f;
-    if (b < B && r < rows) {
-      const long long dr = p.idx ? p.idx[b] : b;
-      x = p.data[dr * p.ld_data + row0 + r];
+  // the minibatch row numbers first (one dependent load for everybody), then eight gathers in flight per thread
+  int* sidx = reinterpret_cast<int*>(misc) + 32;
+  if (tid < BTS) sidx[tid] = tid < B ? (p.idx ? p.idx[tid] : tid) : -1;
+  __syncthreads();
+  {
+    constexpr int UG = 8;
+    const int n = p.rows_alloc * BTS;
+    for (int e0 = tid; e0 < n; e0 += UG * NT) {
+      float x[UG];
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
+        x[u] = 0.f;
+        if (e < n && r < rows) {
+          const int dr = sidx[b];
+          if (dr >= 0) x[u] = __ldg(&p.data[(long long)dr * p.ld_data + row0 + r]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
+        if (e < n) {
+          v0s[r * BTS + b] = x[u];
+          nvs[r * BTS + b] = p.pcd ? roundf(x[u]) : 0.f;   // src/rbm.py:428; the nv slab is free until the last Gibbs step
+        }
+      }
     }
-    v0s[r * BTS + b] = x;
-    nvs[r * BTS + b] = p.pcd ? roundf(x) : 0.f;   // src/rbm.py:428; the nv slab is free until the last Gibbs step
   }
   __syncthreads();
   mark();   // gather done
 
-  // ---- propup of one staged tile: acc[b] += src[r][b] * W[r, 4q..4q+3]; DUAL shares the W loads ----
+  // ---- propup of one staged tile: acc[b][4q..4q+3] += src[r][b] * W[r, 4q..4q+3]; DUAL shares the W loads.
+  //      Packed FFMA2: an accumulator pair is (row b, row b+1) of one column, the v pair comes straight out
+  //      of the LDS.128, the weight is duplicated.  Two rows are in flight per iteration: with two warps per
+  //      scheduler the shared-memory latency is otherwise exposed (scripts/ubench/up_rate*.cu) ----
+  auto fma_row = [&](const float4& w, const float4 (&v)[BTP / 4], float2 (&acc)[BTP / 2][4]) {
+    const float2 wd[4] = {make_float2(w.x, w.x), make_float2(w.y, w.y), make_float2(w.z, w.z), make_float2(w.w, w.w)};
+#pragma unroll
+    for (int b4 = 0; b4 < BTP / 4; ++b4) {
+      const float2 p0 = make_float2(v[b4].x, v[b4].y), p1 = make_float2(v[b4].z, v[b4].w);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[2 * b4][c] = __ffma2_rn(p0, wd[c], acc[2 * b4][c]);
+        if (4 * b4 + 2 < BT) acc[2 * b4 + 1][c] = __ffma2_rn(p1, wd[c], acc[2 * b4 + 1][c]);
+      }
+    }
+  };
   auto up_tile = [&](const unsigned char* __restrict__ tile, const float* __restrict__ src,
-                     const float* __restrict__ src2, int nr, float4 (&acc)[BT], float4 (&acc2)[BT], bool dual) {
+                     const float* __restrict__ src2, int nr, float2 (&acc)[BTP / 2][4], float2 (&acc2)[BTP / 2][4],
+                     bool dual) {
     if (!col_ok) return;
     const unsigned char* bp = tile + (q >> 3) * box_bytes;
-    const int c = q & 7;
-    for (int r = g; r < nr; r += p.G) {
-      const float4 w = *reinterpret_cast<const float4*>(bp + r * 128 + ((c ^ (r & 7)) << 4));
-      const float4* vr = reinterpret_cast<const float4*>(src + r * BTS);
+    const int c = q & 7, G = p.G;
+    auto ldw_ = [&](int r) { return *reinterpret_cast<const float4*>(bp + r * 128 + ((c ^ (r & 7)) << 4)); };
+    int r = g;
+    for (; r + G < nr; r += 2 * G) {
+      const float4 w0 = ldw_(r), w1 = ldw_(r + G);
+      float4 v0[BTP / 4], v1[BTP / 4], x0[BTP / 4], x1[BTP / 4];
 #pragma unroll
       for (int b4 = 0; b4 < BTP / 4; ++b4) {
-        const float4 vv = vr[b4];
-        const float xs[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int b = b4 * 4 + t;
-          if (b < BT) {
-            acc[b].x = fmaf(xs[t], w.x, acc[b].x);
-            acc[b].y = fmaf(xs[t], w.y, acc[b].y);
-            acc[b].z = fmaf(xs[t], w.z, acc[b].z);
-            acc[b].w = fmaf(xs[t], w.w, acc[b].w);
-          }
-        }
+        v0[b4] = reinterpret_cast<const float4*>(src + r * BTS)[b4];
+        v1[b4] = reinterpret_cast<const float4*>(src + (r + G) * BTS)[b4];
       }
       if (dual) {
-        const float4* xr = reinterpret_cast<const float4*>(src2 + r * BTS);
 #pragma unroll
         for (int b4 = 0; b4 < BTP / 4; ++b4) {
-          const float4 vv = xr[b4];
-          const float xs[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int b = b4 * 4 + t;
-            if (b < BT) {
-              acc2[b].x = fmaf(xs[t], w.x, acc2[b].x);
-              acc2[b].y = fmaf(xs[t], w.y, acc2[b].y);
-              acc2[b].z = fmaf(xs[t], w.z, acc2[b].z);
-              acc2[b].w = fmaf(xs[t], w.w, acc2[b].w);
-            }
-          }
+          x0[b4] = reinterpret_cast<const float4*>(src2 + r * BTS)[b4];
+          x1[b4] = reinterpret_cast<const float4*>(src2 + (r + G) * BTS)[b4];
         }
+      }
+      fma_row(w0, v0, acc);
+      fma_row(w1, v1, acc);
+      if (dual) {
+        fma_row(w0, x0, acc2);
+        fma_row(w1, x1, acc2);
+      }
+    }
+    if (r < nr) {
+      const float4 w0 = ldw_(r);
+      float4 v0[BTP / 4];
+#pragma unroll
+      for (int b4 = 0; b4 < BTP / 4; ++b4) v0[b4] = reinterpret_cast<const float4*>(src + r * BTS)[b4];
+      fma_row(w0, v0, acc);
+      if (dual) {
+#pragma unroll
+        for (int b4 = 0; b4 < BTP / 4; ++b4) v0[b4] = reinterpret_cast<const float4*>(src2 + r * BTS)[b4];
+        fma_row(w0, v0, acc2);
       }
     }
   };
 
-  // ---- CTA partial [BT][ldw]: sum over the G row groups (fixed order), then to global scratch ---
-  // uses hs as the staging accumulator (it is reloaded after the reduction anyway)
-  auto flush_partial = [&](float4 (&acc)[BT], int set) {
+  // ---- CTA partial [B][H] -> grid-wide sum: the G row groups are added in shared memory (fixed order, hs is
+  //      the staging buffer: it is rebuilt from the sums afterwards anyway), then every element goes to the
+  //      fixed-point accumulator with one red.global.add.u64; CTAs start at staggered offsets ----
+  auto flush_sums = [&](float2 (&acc)[BTP / 2][4], unsigned long long* dst) {
     float4* stage = reinterpret_cast<float4*>(hs);
     const int ldh4 = ldh >> 2;
     for (int gg = 0; gg < p.G; ++gg) {
       if (col_ok && g == gg) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          float4 a = acc[b];
+          float4 a = (b & 1) ? make_float4(acc[b >> 1][0].y, acc[b >> 1][1].y, acc[b >> 1][2].y, acc[b >> 1][3].y)
+                             : make_float4(acc[b >> 1][0].x, acc[b >> 1][1].x, acc[b >> 1][2].x, acc[b >> 1][3].x);
           if (gg > 0) {
             const float4 o = stage[b * ldh4 + q];
             a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
@@ -289,133 +351,165 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       __syncthreads();
     }
     if (rows > 0) {
-      float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)cta * 2 + set) * BT * ldw);
-      const int ldw4 = ldw >> 2;
-      for (int e = tid; e < BT * p.CQ; e += NT) {
-        const int b = e / p.CQ, qq = e - b * p.CQ;
-        __stcg(&dst[b * ldw4 + qq], stage[b * ldh4 + qq]);
+      // flat walk over the B*H elements from a CTA-specific offset (spreads the CTAs over the addresses);
+      // (b, j) advance incrementally: no division in the loop
+      const int total = B * H;
+      int e = tid + (int)(((long long)cta * total) / gridDim.x);
+      if (e >= total) e -= total;
+      int b = e / H, j = e - b * H;
+      for (int i = tid; i < total; i += NT) {
+        red_add_u64(dst + b * ldw + j, to_fixed(hs[b * ldh + j]));
+        j += NT;
+        while (j >= H) { j -= H; if (++b == B) b = 0; }
       }
     }
     __syncthreads();
   };
 
-  // ---- distributed reduction of the hidden pre-activations + epilogue ----------------
-  //  set 0: pre = sum + hb -> mean (sigmoid) -> mean_out, sample -> HS (and P on the last PCD step)
-  //  set 1: PREX = sum + hb (pre-activation of round(v0), pseudo-likelihood)
-  auto reduce_hidden = [&](int nsets, float* mean_out, const RngSeg& rs, bool write_hs, bool write_p) {
-    const int ldw4 = ldw >> 2;
-    const int nq = nsets * BT * p.CQ;
-    const int per = (nq + gridDim.x - 1) / gridDim.x;
-    const int o0 = cta * per, o1 = min(nq, o0 + per);
-    for (int o = o0 + warp; o < o1; o += NWARP) {
-      int set = o / (BT * p.CQ), rem = o % (BT * p.CQ);
-      int b = rem / p.CQ, qq = rem % p.CQ;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      // up to 8 partials per lane (grids up to 256 CTAs): all loads in flight at once, summed in order
-      float4 t8[8];
+  // ---- summed pre-activations -> hs as fp32 (no bias yet): [B][H] quads, eight L2 loads in flight per
+  //      thread.  Rows b >= B are zero.  The consumers below are COMPACT loops over shared memory: this code
+  //      runs once per pass, so straight-line unrolled math would be bound by instruction fetch ----
+  auto sums_to_hs = [&](const unsigned long long* src) {
+    constexpr int UB = 8;
+    const int n = BT * p.CQ;
+    for (int e0 = tid; e0 < n; e0 += UB * NT) {
+      longlong2 t[UB][2];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = lane + 32 * u;
-        t8[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < p.n_active)
-          t8[u] = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)c * 2 + set) * BT * ldw) + b * ldw4 + qq);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { s.x += t8[u].x; s.y += t8[u].y; s.z += t8[u].z; s.w += t8[u].w; }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
-        s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
-        s.z += __shfl_xor_sync(0xffffffffu, s.z, off);
-        s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
-      }
-      if (lane < 4) {
-        float sv = lane == 0 ? s.x : lane == 1 ? s.y : lane == 2 ? s.z : s.w;
-        int j = qq * 4 + lane;
-        if (j < H) {
-          float pre = sv + p.hb[j];
-          if (set == 1) {
-            __stcg(&p.PREX[b * ldw + j], pre);
-          } else {
-            float mean = 0.f, smp = 0.f;
-            if (b < B) {
-              mean = sigmoidf_(pre);
-              if (write_hs || write_p) smp = rng_uniform(rs, (long long)b * H + j) < mean ? 1.f : 0.f;
-            }
-            __stcg(&mean_out[b * ldw + j], mean);
-            if (write_hs) __stcg(&p.HS[b * ldw + j], smp);
-            if (write_p && b < B) __stcg(&p.P[(size_t)b * H + j], smp);
-          }
-        }
-      }
-    }
-  };
-
-  // chain state [BT][ldw] from L2 into the shared-memory panel (float4, four loads in flight per thread)
-  auto load_hs = [&](const float* src, int ld_src, int nrows_src) {
-    const int ldw4 = ldw >> 2, n4 = BT * ldw4;
-    const bool vec = (ld_src & 3) == 0 && (((uintptr_t)src) & 15) == 0;
-    for (int e0 = tid; e0 < n4; e0 += 4 * NT) {
-      float4 x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * NT;
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < n4) {
-          const int b = e / ldw4, j = (e - b * ldw4) * 4;
-          if (b < nrows_src) {
-            const float* sp = src + (size_t)b * ld_src + j;
-            if (vec && j + 3 < H) x[u] = __ldcg(reinterpret_cast<const float4*>(sp));
-            else {
-              if (j < H) x[u].x = __ldcg(sp);
-              if (j + 1 < H) x[u].y = __ldcg(sp + 1);
-              if (j + 2 < H) x[u].z = __ldcg(sp + 2);
-              if (j + 3 < H) x[u].w = __ldcg(sp + 3);
-            }
-          }
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * NT, b = e / p.CQ, qq = e - b * p.CQ;
+        t[u][0] = t[u][1] = make_longlong2(0, 0);
+        if (e < n && b < B) {
+          const longlong2* sp = reinterpret_cast<const longlong2*>(src + b * ldw + 4 * qq);
+          t[u][0] = __ldcg(sp);
+          t[u][1] = __ldcg(sp + 1);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * NT;
-        if (e < n4) {
-          const int b = e / ldw4, j = (e - b * ldw4) * 4;
-          *reinterpret_cast<float4*>(hs + b * ldh + j) = x[u];
-        }
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * NT, b = e / p.CQ, qq = e - b * p.CQ;
+        if (e < n)
+          *reinterpret_cast<float4*>(hs + b * ldh + 4 * qq) =
+              make_float4(from_fixed(t[u][0].x), from_fixed(t[u][0].y), from_fixed(t[u][1].x), from_fixed(t[u][1].y));
       }
     }
     __syncthreads();
   };
+  // ---- hidden layer from the summed pre-activations: mean = sigmoid(sum + hb), sample ~ Bernoulli(mean) into
+  //      the shared-memory chain state.  EVERY CTA does this for the whole [B][H] (the draws are indexed by
+  //      element, so all CTAs get the same sample); the last CTA also stores the persistent chain ----
+  auto hidden_from_sums = [&](const unsigned long long* src, const RngSeg& rs, bool write_p) {
+    sums_to_hs(src);
+    const bool quad_rng = rs.mode != MDBN_RNG_BUFFER && (H & 3) == 0;
+    const int n = B * p.CQ;
+#pragma unroll 1
+    for (int e = tid; e < n; e += NT) {
+      const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+      float4* hp = reinterpret_cast<float4*>(hs + b * ldh + j0);
+      const float4 x = *hp, hb4 = *reinterpret_cast<const float4*>(hbs + j0);
+      const float mean[4] = {sigmoid_fast_(x.x + hb4.x), sigmoid_fast_(x.y + hb4.y), sigmoid_fast_(x.z + hb4.z),
+                             sigmoid_fast_(x.w + hb4.w)};
+      float u[4];
+      if (quad_rng) {
+        const long long e0 = (long long)b * H + j0;     // multiple of 4: one Philox block serves the quad
+        const Philox4 ph4 = philox4x32_10((uint32_t)(e0 >> 2), rs.c1, rs.c2, rs.c3, rs.k0, rs.k1);
+        u[0] = u24(ph4.x); u[1] = u24(ph4.y); u[2] = u24(ph4.z); u[3] = u24(ph4.w);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) u[t] = j0 + t < H ? rng_uniform(rs, (long long)b * H + j0 + t) : 2.f;
+      }
+      float sm4[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        sm4[t] = (j0 + t < H && u[t] < mean[t]) ? 1.f : 0.f;
+        if (write_p && j0 + t < H) p.P[(size_t)b * H + j0 + t] = sm4[t];
+      }
+      *hp = make_float4(sm4[0], sm4[1], sm4[2], sm4[3]);
+    }
+    __syncthreads();
+  };
+  // hidden means of a sum buffer into hs (statistics pass: every thread then picks up its own columns)
+  auto means_to_hs = [&](const unsigned long long* src) {
+    sums_to_hs(src);
+    const int n = B * p.CQ;
+#pragma unroll 1
+    for (int e = tid; e < n; e += NT) {
+      const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+      float4* hp = reinterpret_cast<float4*>(hs + b * ldh + j0);
+      const float4 x = *hp, hb4 = *reinterpret_cast<const float4*>(hbs + j0);
+      *hp = make_float4(sigmoid_fast_(x.x + hb4.x), sigmoid_fast_(x.y + hb4.y), sigmoid_fast_(x.z + hb4.z),
+                        sigmoid_fast_(x.w + hb4.w));
+    }
+    __syncthreads();
+  };
+  // PCD: chain state from the persistent chain [B][H] (src/rbm.py:308-311)
+  auto load_chain = [&]() {
+    const bool vec = (H & 3) == 0 && (((uintptr_t)p.P) & 15) == 0;
+    for (int e = tid; e < BT * p.CQ; e += NT) {
+      const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B) {
+        const float* sp = p.P + (size_t)b * H + j0;
+        if (vec && j0 + 3 < H) x = __ldcg(reinterpret_cast<const float4*>(sp));
+        else {
+          if (j0 < H) x.x = __ldcg(sp);
+          if (j0 + 1 < H) x.y = __ldcg(sp + 1);
+          if (j0 + 2 < H) x.z = __ldcg(sp + 2);
+          if (j0 + 3 < H) x.w = __ldcg(sp + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(hs + b * ldh + j0) = x;
+    }
+    __syncthreads();
+  };
+  unsigned long long* const A0 = p.acc;
+  unsigned long long* const A1 = p.acc + p.n_acc;
+  auto GA = [&](int s) { return p.acc + (size_t)(2 + s % 3) * p.n_acc; };
 
   // =============================== pass 0: positive phase ===============================
   {
     const int depth = p.nslots;
-    if (warp == 0 && !(F & 2)) for (int j = 1; j < depth; ++j) issue(j, depth);
-    float4 acc[BT], acc2[BT];
+    if (!(F & 2)) for (int j = 1; j < depth; ++j) issue(j, depth);
+    float2 acc[BTP / 2][4], acc2[BTP / 2][4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = acc2[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < BTP / 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[b][c] = acc2[b][c] = make_float2(0.f, 0.f);
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
       if (!(F & 2)) wait_stage(st);
       const unsigned char* tile = smem + (size_t)st * p.slot_bytes;
       const int nr = min(R, rows - j * R);
       if (!(F & 1)) up_tile(tile, v0s + (size_t)j * R * BTS, nvs + (size_t)j * R * BTS, nr, acc, acc2, p.pcd != 0);
       __syncthreads();
-      if (warp == 0 && !(F & 2)) issue(j + depth, depth);
+      if (!(F & 2)) issue(j + depth, depth);
     }
     mark();   // pass-0 tiles done
-    flush_partial(acc, 0);
-    if (p.pcd) flush_partial(acc2, 1);
+    flush_sums(acc, A0);
+    if (p.pcd) flush_sums(acc2, A1);
   }
   mark();
   grid_sync(p.bar, bar_target);
   mark();
+  if (!(F & 32)) issue(0, p.nslots);     // W is unchanged until the update: prefetch the next pass now
   // CD: chain starts from the fresh sample; PCD: from the persistent chain (src/rbm.py:308-311)
-  reduce_hidden(p.pcd ? 2 : 1, p.PH, seg(0, 0), !p.pcd, false);
-  mark();   // reduce 0 done
-  grid_sync(p.bar, bar_target);
-  if (warp == 0 && !(F & 32)) issue(0, p.nslots);     // W is unchanged until the update: prefetch the next pass now
-  if (p.pcd) load_hs(p.P, H, B); else load_hs(p.HS, ldw, BT);
-  mark();
+  if (p.pcd) load_chain(); else hidden_from_sums(A0, seg(0, 0), false);
+  mark();   // chain state ready
+  // positive-phase means as fp32 for the statistics pass: every CTA converts one slice (published by the
+  // barriers that follow), so that pass does not pay a second sum -> mean round trip
+  {
+    const int per = (BT * p.CQ + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int i = tid; i < per && cta * per + i < BT * p.CQ; i += NT) {
+      const int e = cta * per + i, b = e / p.CQ, qq = e - b * p.CQ;
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B) {
+        const longlong2* sp = reinterpret_cast<const longlong2*>(A0 + b * ldw + 4 * qq);
+        const longlong2 s01 = __ldcg(sp), s23 = __ldcg(sp + 1);
+        const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * qq);
+        m = make_float4(sigmoid_fast_(from_fixed(s01.x) + hb4.x), sigmoid_fast_(from_fixed(s01.y) + hb4.y),
+                        sigmoid_fast_(from_fixed(s23.x) + hb4.z), sigmoid_fast_(from_fixed(s23.y) + hb4.w));
+      }
+      __stcg(reinterpret_cast<float4*>(p.PHf + b * ldw + 4 * qq), m);
+    }
+  }
 
   // pseudo-likelihood monitor (src/rbm.py:421-447), pre-update W, hb, vb: one minibatch row per CTA, taken
   // from the END of the grid (the last CTA owns the fewest rows); its loads overlap the tile prefetch above
@@ -427,7 +521,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       const float d = 1.f - 2.f * x;
       float h0 = 0.f, h1 = 0.f;
       for (int j = tid; j < H; j += NT) {
-        const float pre = __ldcg(&p.PREX[b * ldw + j]);
+        const float pre = from_fixed((long long)__ldcg(&A1[b * ldw + j])) + hbs[j];
         h0 += softplusf_(pre);
         h1 += softplusf_(pre + d * p.W[(size_t)bit * ldw + j]);
       }
@@ -451,46 +545,87 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s);
     const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s);
     const int depth = p.nslots;
-    if (warp == 0 && !(F & 32)) for (int j = 1; j < depth; ++j) issue(j, depth);   // job 0 was prefetched
-    float4 acc[BT];
+    if (!(F & 32)) for (int j = 1; j < depth; ++j) issue(j, depth);   // job 0 was prefetched
+    float2 acc[BTP / 2][4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < BTP / 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[b][c] = make_float2(0.f, 0.f);
 
     for (int j = 0, st = 0; j < ntiles; ++j, st = (st + 1 == depth ? 0 : st + 1)) {
       if (!(F & 32)) wait_stage(st);
       const unsigned char* tile = smem + (size_t)st * p.slot_bytes;
       const int nr = min(R, rows - j * R);
       // ---- propdown of the tile rows, lane = row: out[b] = sum_j h[b][j] W[row][j] stays in one thread;
-      //      the warps (and, for short tiles, the lane groups) split the boxes of 32 columns ----
+      //      the warps (and lane groups) split the boxes of 32 columns.  This phase is bound by the
+      //      shared-memory wavefronts of the h broadcasts, so with full tiles (R = 32) a lane takes TWO rows
+      //      (l and l+16; the half-warps work on different boxes): every h load then feeds 8 FMAs ----
       if (!(F & 4)) {
-        float dacc[BT];
+        if (R == 32) {
+          const int lr = lane & 15, half = lane >> 4;
+          float da[BT], db[BT];
 #pragma unroll
-        for (int b = 0; b < BT; ++b) dacc[b] = 0.f;
-        for (int bx = warp * SUBS + dsub; bx < nbox; bx += NWARP * SUBS) {
-          const unsigned char* bp = tile + bx * box_bytes + drow * 128;
-          const float* hb0 = hs + bx * 32;
+          for (int b = 0; b < BT; ++b) da[b] = db[b] = 0.f;
+          for (int bx = warp * 2 + half; bx < nbox; bx += NWARP * 2) {
+            const unsigned char* bpa = tile + bx * box_bytes + lr * 128;
+            const float* hb0 = hs + bx * 32;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 w = *reinterpret_cast<const float4*>(bp + ((c ^ (drow & 7)) << 4));
+            for (int c = 0; c < 8; ++c) {
+              const int sw = (c ^ (lr & 7)) << 4;                                  // rows l and l+16 swizzle alike
+              const float4 wa = *reinterpret_cast<const float4*>(bpa + sw);
+              const float4 wb = *reinterpret_cast<const float4*>(bpa + 16 * 128 + sw);
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-              const float4 h4 = *reinterpret_cast<const float4*>(hb0 + b * ldh + c * 4);     // warp-broadcast
-              dacc[b] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, dacc[b]))));
+              for (int b = 0; b < BT; ++b) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hb0 + b * ldh + c * 4);   // broadcast per half-warp
+                da[b] = fmaf(h4.x, wa.x, fmaf(h4.y, wa.y, fmaf(h4.z, wa.z, fmaf(h4.w, wa.w, da[b]))));
+                db[b] = fmaf(h4.x, wb.x, fmaf(h4.y, wb.y, fmaf(h4.z, wb.z, fmaf(h4.w, wb.w, db[b]))));
+              }
             }
           }
-        }
-        float* d0 = dred + (size_t)(warp * SUBS + dsub) * BT * R + drow;
+          // the two half-warps hold partials of the same 32 rows: add them, lanes 0-15 store both rows
 #pragma unroll
-        for (int b = 0; b < BT; ++b) d0[b * R] = dacc[b];
+          for (int b = 0; b < BT; ++b) {
+            da[b] += __shfl_xor_sync(0xffffffffu, da[b], 16);
+            db[b] += __shfl_xor_sync(0xffffffffu, db[b], 16);
+          }
+          if (half == 0) {
+            float* d0 = dred + (size_t)warp * BT * 32 + lr;
+#pragma unroll
+            for (int b = 0; b < BT; ++b) { d0[b * 32] = da[b]; d0[b * 32 + 16] = db[b]; }
+          }
+        } else {
+          float dacc[BT];
+#pragma unroll
+          for (int b = 0; b < BT; ++b) dacc[b] = 0.f;
+          for (int bx = warp * SUBS + dsub; bx < nbox; bx += NWARP * SUBS) {
+            const unsigned char* bp = tile + bx * box_bytes + drow * 128;
+            const float* hb0 = hs + bx * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 w = *reinterpret_cast<const float4*>(bp + ((c ^ (drow & 7)) << 4));
+#pragma unroll
+              for (int b = 0; b < BT; ++b) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hb0 + b * ldh + c * 4);     // warp-broadcast
+                dacc[b] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, dacc[b]))));
+              }
+            }
+          }
+          float* d0 = dred + (size_t)(warp * SUBS + dsub) * BT * R + drow;
+#pragma unroll
+          for (int b = 0; b < BT; ++b) d0[b * R] = dacc[b];
+        }
       }
       __syncthreads();
-      // ---- visible epilogue: bias, activation, sampling (src/rbm.py:226-240 / :650-660) ----
-      for (int it = tid; it < nr * BTS && !(F & 8); it += NT) {
-        const int r = it / BTS, b = it - r * BTS;
+      // ---- visible epilogue: bias, activation, sampling (src/rbm.py:226-240 / :650-660); consecutive threads
+      //      take consecutive rows so that the partial sums are read without bank conflicts ----
+      const int nparts = R == 32 ? NWARP : NWARP * SUBS;
+      for (int it = tid; it < R * BTS && !(F & 8); it += NT) {
+        const int b = it / R, r = it & (R - 1);
+        if (r >= nr) continue;
         float vin = 0.f, mean = 0.f;
         if (b < B) {
           float sum = 0.f;
-          for (int w2 = 0; w2 < NWARP * SUBS; ++w2) sum += dred[((size_t)w2 * BT + b) * R + r];
+          for (int w2 = 0; w2 < nparts; ++w2) sum += dred[((size_t)w2 * BT + b) * R + r];
           const int lr_ = j * R + r;
           const float pre = sum + vbs[lr_];
           if (p.kind == MDBN_GRBM) {
@@ -513,22 +648,28 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       // ---- propup accumulation from the same tile ----
       if (!(F & 16)) up_tile(tile, vt, vt, nr, acc, acc, false);
       __syncthreads();
-      if (warp == 0 && !(F & 32)) issue(j + depth, depth);
+      if (!(F & 32)) issue(j + depth, depth);
     }
     if (last) mark();   // Gibbs tiles done
-    flush_partial(acc, 0);
+    // accumulator of step s+1 was last used by step s-2 of THIS launch: everybody finished reading it before
+    // the previous barrier, nobody adds to it before the next one
+    if (s >= 2 && s + 1 < p.k) {
+      unsigned long long* z = GA(s + 1);
+      for (int i = cta * NT + tid; i < p.n_acc; i += gridDim.x * NT) __stcg(&z[i], 0ULL);
+    }
+    flush_sums(acc, GA(s));
     if (last && !p.pcd) {
       const float c = block_sum(cost_acc, misc);
       if (tid == 0) __stcg(&p.cost_part[cta], c);
     }
-    grid_sync(p.bar, bar_target);
     if (last) mark();
-    reduce_hidden(1, p.NH, rs_h, !last, last && p.pcd);
     grid_sync(p.bar, bar_target);
     if (last) mark();
     if (!last) {
-      if (warp == 0 && !(F & 32)) issue(0, p.nslots);
-      load_hs(p.HS, ldw, BT);
+      if (!(F & 32)) issue(0, p.nslots);
+      hidden_from_sums(GA(s), rs_h, false);
+    } else if (p.pcd && cta == (int)gridDim.x - 1) {
+      hidden_from_sums(GA(s), rs_h, true);     // new persistent chain (src/rbm.py:372)
     }
   }
 
@@ -541,17 +682,15 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     depth = depth > MAX_SLOTS ? MAX_SLOTS : depth;
     const int ntiles_s = (rows + TRS - 1) / TRS;
     if (warp == 0) for (int j = 0; j < depth; ++j) issue_rows(j, narr, depth, TRS, slot_s);
-    const int ldw4 = ldw >> 2, ldw4x = ldw >> 2;
+    const int ldw4x = ldw >> 2;
     float4 ph[BT], nh[BT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) {
-      if (col_ok) {
-        ph[b] = __ldcg(reinterpret_cast<const float4*>(p.PH) + b * ldw4 + q);
-        nh[b] = __ldcg(reinterpret_cast<const float4*>(p.NH) + b * ldw4 + q);
-      } else {
-        ph[b] = nh[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    for (int b = 0; b < BT; ++b)
+      ph[b] = col_ok ? __ldcg(reinterpret_cast<const float4*>(p.PHf + b * ldw + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    means_to_hs(GA(p.k - 1));
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+      nh[b] = col_ok ? *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int ncol = min(4, H - 4 * q);
     for (int j = 0, stg = 0; j < ntiles_s; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
       wait_stage(stg);
@@ -561,6 +700,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       const float4* sn = reinterpret_cast<const float4*>(sb + 2 * (size_t)slot_s);
       const int nr = min(TRS, rows - j * TRS);
       if (col_ok) {
+        // (measured: packed FFMA2 and two rows in flight are both SLOWER here than this plain loop)
         for (int r = g; r < nr; r += p.G) {
           const int lr_ = j * TRS + r;
           float4 w = wt[r * ldw4x + q], sp = st[r * ldw4x + q];
@@ -591,8 +731,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
             float gw = gv[c] * p.inv_bnom - p.wc * snv[c];                // src/rbm.py:411-415
             float mult = p.decay;
             if (p.c1 != 0.f) {
-              // D = 1 + 2 lr lambda_1 / (|W| + eps); MUFU reciprocals (<= 2 ulp) instead of IEEE division
-              float invD = __fdividef(1.0f, 1.0f + p.c1 * __fdividef(1.0f, fabsf(wv[c]) + 0.001f));   // :347-350
+              // 1/D, D = 1 + 2 lr lambda_1 / (|W| + eps)  ==  (|W| + eps) / (|W| + eps + 2 lr lambda_1):
+              // ONE MUFU reciprocal (<= 1 ulp) instead of two IEEE divisions                      :347-350
+              const float t = fabsf(wv[c]) + 0.001f;
+              const float invD = t * rcp_approx(t + p.c1);
               gw *= invD;
               mult *= invD;                                               // :353-356
             }
@@ -621,14 +763,25 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       p.Svb[row0 + r] = gb + (sv - gb) * p.mom;
       p.vb[row0 + r] = p.vb[row0 + r] + sv * p.lr;
     }
-    // hidden bias  src/rbm.py:416 — one CTA (the last: it owns the fewest rows)
-    if (cta == gridDim.x - 1) {
-      for (int j = tid; j < H; j += NT) {
-        float gsum = 0.f;
-        for (int b = 0; b < B; ++b) gsum += __ldcg(&p.PH[b * ldw + j]) - __ldcg(&p.NH[b * ldw + j]);
-        float gb = gsum * p.inv_b, sv = p.Shb[j];
-        p.Shb[j] = gb + (sv - gb) * p.mom;
-        p.hb[j] = p.hb[j] + sv * p.lr;
+    // hidden bias  src/rbm.py:416 — one CTA (the last: it owns the fewest rows), from the means already in
+    // the registers of row group 0
+    if (cta == (int)gridDim.x - 1 && col_ok && g == 0) {
+      float gs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        if (b < B) {
+          gs4[0] += ph[b].x - nh[b].x; gs4[1] += ph[b].y - nh[b].y;
+          gs4[2] += ph[b].z - nh[b].z; gs4[3] += ph[b].w - nh[b].w;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = 4 * q + t;
+        if (j < H) {
+          const float gb = gs4[t] * p.inv_b, sv = p.Shb[j];
+          p.Shb[j] = gb + (sv - gb) * p.mom;
+          p.hb[j] = hbs[j] + sv * p.lr;
+        }
       }
     }
     if (cta == 0 && tid == 0) {
@@ -690,7 +843,7 @@ static int make_map(CUtensorMap* tm, const float* W, int V, int ldw, int box_row
 
 struct Geometry {
   int BT, rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, grid, ldh, slot_bytes, ring_bytes;
-  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb;
+  int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb, off_hb;
   size_t smem;
   bool ok;
 };
@@ -720,8 +873,8 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
   const size_t hs_b = up128((size_t)g.BT * g.ldh * 4), slab_b = up128((size_t)g.rows_alloc * BTS * 4),
                vt_b = up128((size_t)32 * BTS * 4), dred_b = up128((size_t)NWARP * 32 * g.BT * 4),
-               vb_b = up128((size_t)g.rows_alloc * 4);
-  const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256 + vb_b;
+               vb_b = up128((size_t)g.rows_alloc * 4), hb_b = up128((size_t)g.ldh * 4);
+  const size_t fixed = hs_b + 2 * slab_b + vt_b + dred_b + 128 + 256 + vb_b + hb_b;
   const size_t smem_max = 227 * 1024;
   if (fixed + 2 * (size_t)g.slot_bytes > smem_max) return g;
   g.nslots = (int)((smem_max - fixed) / g.slot_bytes);
@@ -739,6 +892,7 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.off_bars = take(128);
   g.off_misc = take(256);
   g.off_vb = take(vb_b);
+  g.off_hb = take(hb_b);
   g.smem = off;
   g.ok = g.smem <= smem_max;
   return g;
@@ -791,31 +945,30 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.R = g.R; p.nbox = g.nbox; p.nslots = g.nslots;
   p.ldh = g.ldh; p.slot_bytes = g.slot_bytes; p.ring_bytes = g.ring_bytes;
   p.off_hs = g.off_hs; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vt = g.off_vt; p.off_dred = g.off_dred;
-  p.off_bars = g.off_bars; p.off_misc = g.off_misc; p.off_vb = g.off_vb;
+  p.off_bars = g.off_bars; p.off_misc = g.off_misc; p.off_vb = g.off_vb; p.off_hb = g.off_hb;
 
-  // scratch: [part | PH | NH | HS | PREX | cost_part]; zero-filled whenever (re)allocated so that
-  // padded columns of the [BT][ldw] buffers stay zero
-  const size_t hb_f = (size_t)g.BT * a.ldw;
-  const size_t part_f = (size_t)g.n_active * 2 * hb_f;
-  const size_t total_f = part_f + 4 * hb_f + (size_t)g.grid + 64;
+  // scratch: two sets of 5 fixed-point accumulators [BT][ldw] + cost partials.  A launch works in one set
+  // (zero on entry) and clears the other; everything is re-zeroed when the layout changes.
+  const size_t n_acc = (size_t)g.BT * a.ldw;
+  const size_t total_b = 2 * 5 * n_acc * sizeof(unsigned long long) + ((size_t)g.grid + 64 + n_acc) * sizeof(float);
   mdbn_ctx::Buf& wb = c->ws[WS_SKINNY];
   const void* before = wb.p;
   const size_t before_n = wb.n;
-  float* base = (float*)ws_get(c, WS_SKINNY, total_f * sizeof(float));
+  unsigned long long* base = (unsigned long long*)ws_get(c, WS_SKINNY, total_b);
   if (!base) return 3;
-  static thread_local unsigned long long last_key = 0;
   const unsigned long long key = ((unsigned long long)g.BT << 48) ^ ((unsigned long long)a.ldw << 24) ^
-                                 (unsigned long long)g.n_active ^ ((unsigned long long)(uintptr_t)base << 1);
-  if (before != wb.p || before_n != wb.n || key != last_key) {
+                                 ((unsigned long long)(uintptr_t)base << 1) ^ 1ULL;
+  if (before != wb.p || before_n != wb.n || key != c->skinny_key) {
     MDBN_CUDA(cudaMemsetAsync(base, 0, wb.n, st));
-    last_key = key;
+    c->skinny_key = key;
+    c->skinny_parity = 0;
   }
-  p.part = base;
-  p.PH = base + part_f;
-  p.NH = p.PH + hb_f;
-  p.HS = p.NH + hb_f;
-  p.PREX = p.HS + hb_f;
-  p.cost_part = p.PREX + hb_f;
+  p.n_acc = (int)n_acc;
+  p.acc = base + (size_t)c->skinny_parity * 5 * n_acc;
+  p.acc_other = base + (size_t)(1 - c->skinny_parity) * 5 * n_acc;
+  c->skinny_parity ^= 1u;
+  p.cost_part = reinterpret_cast<float*>(base + 2 * 5 * n_acc);
+  p.PHf = p.cost_part + g.grid + 64;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
   static const int dbg_flags = getenv("MDBN_SKINNY_DEBUG") ? atoi(getenv("MDBN_SKINNY_DEBUG")) : 0;
