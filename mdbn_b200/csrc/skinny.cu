@@ -51,7 +51,7 @@ struct Params {
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
   // geometry
-  int rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, ldh, slot_bytes, ring_bytes;
+  int rows_per_cta, rows_small, n_big, rows_alloc, CQ, GW, G, R, nbox, nslots, ldh, slot_bytes, ring_bytes;
   // global scratch: fixed-point (2^-32) accumulators of the hidden pre-activation sums, [5][BT][ldw]:
   // 0 = positive phase, 1 = round(v0) (pseudo-likelihood), 2..4 = Gibbs steps (rotating).  Zero on entry;
   // `acc_other` is the set of the previous launch, cleared by this one.
@@ -134,6 +134,26 @@ __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long
   __syncthreads();
 }
 
+// Split form: arrive as soon as this CTA's contribution is published, keep working, wait later.
+__device__ __forceinline__ void grid_arrive(unsigned long long* bar, unsigned long long& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1ULL);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned long long* bar, unsigned long long target) {
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <int BT>
 __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant__ CUtensorMap tmR,
                                                           const __grid_constant__ CUtensorMap tm8, const Params p) {
@@ -153,8 +173,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   const int cta = blockIdx.x;
   const int ldw = p.ldw, ldh = p.ldh, R = p.R, nbox = p.nbox;
   const int B = p.B, V = p.V, H = p.H;
-  const int row0 = cta * p.rows_per_cta;
-  const int rows = max(0, min(p.rows_per_cta, V - row0));
+  // CTAs [0, n_big) own rows_per_cta rows each, the rest rows_small (PCD: the monitor CTAs get fewer rows)
+  const int row0 = cta < p.n_big ? cta * p.rows_per_cta : p.n_big * p.rows_per_cta + (cta - p.n_big) * p.rows_small;
+  const int rows = max(0, min(cta < p.n_big ? p.rows_per_cta : p.rows_small, V - row0));
   const int ntiles = (rows + R - 1) / R;
   const int box_bytes = R * 128;
   // propup / statistics mapping: thread -> (row group g, column quad q)
@@ -241,6 +262,17 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   // the minibatch row numbers first (one dependent load for everybody), then eight gathers in flight per thread
   int* sidx = reinterpret_cast<int*>(misc) + 32;
   if (tid < BTS) sidx[tid] = tid < B ? (p.idx ? p.idx[tid] : tid) : -1;
+  // pseudo-likelihood monitor: the CTA that will compute it for minibatch row pl_b fetches its scalars now
+  // (three dependent loads that would otherwise sit on that CTA's critical path)
+  const int pl_b = (int)gridDim.x - 1 - cta;
+  const bool pl_cta = p.pcd && pl_b < B;
+  if (pl_cta && tid == NT - 1) {
+    const int bit = *p.bit_idx;
+    const long long dr = p.idx ? p.idx[pl_b] : pl_b;
+    misc[60] = __int_as_float(bit);
+    misc[61] = roundf(p.data[dr * p.ld_data + bit]);
+    misc[62] = p.vb[bit];
+  }
   __syncthreads();
   {
     constexpr int UG = 8;
@@ -443,21 +475,31 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   };
   // PCD: chain state from the persistent chain [B][H] (src/rbm.py:308-311)
   auto load_chain = [&]() {
+    constexpr int UB = 8;
     const bool vec = (H & 3) == 0 && (((uintptr_t)p.P) & 15) == 0;
-    for (int e = tid; e < BT * p.CQ; e += NT) {
-      const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B) {
-        const float* sp = p.P + (size_t)b * H + j0;
-        if (vec && j0 + 3 < H) x = __ldcg(reinterpret_cast<const float4*>(sp));
-        else {
-          if (j0 < H) x.x = __ldcg(sp);
-          if (j0 + 1 < H) x.y = __ldcg(sp + 1);
-          if (j0 + 2 < H) x.z = __ldcg(sp + 2);
-          if (j0 + 3 < H) x.w = __ldcg(sp + 3);
+    const int n = BT * p.CQ;
+    for (int e0 = tid; e0 < n; e0 += UB * NT) {
+      float4 x[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * NT, b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n && b < B) {
+          const float* sp = p.P + (size_t)b * H + j0;
+          if (vec && j0 + 3 < H) x[u] = __ldcg(reinterpret_cast<const float4*>(sp));
+          else {
+            if (j0 < H) x[u].x = __ldcg(sp);
+            if (j0 + 1 < H) x[u].y = __ldcg(sp + 1);
+            if (j0 + 2 < H) x[u].z = __ldcg(sp + 2);
+            if (j0 + 3 < H) x[u].w = __ldcg(sp + 3);
+          }
         }
       }
-      *reinterpret_cast<float4*>(hs + b * ldh + j0) = x;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int e = e0 + u * NT, b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+        if (e < n) *reinterpret_cast<float4*>(hs + b * ldh + j0) = x[u];
+      }
     }
     __syncthreads();
   };
@@ -484,56 +526,76 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     }
     mark();   // pass-0 tiles done
     flush_sums(acc, A0);
+    grid_arrive(p.bar, bar_target);
+    // the round(v0) sums only feed the pseudo-likelihood monitor: published behind the main barrier on a
+    // counter of their own (bar[2]) that only the CTAs computing the monitor ever wait for
     if (p.pcd) flush_sums(acc2, A1);
   }
   mark();
-  grid_sync(p.bar, bar_target);
+  grid_wait(p.bar, bar_target);
   mark();
   if (!(F & 32)) issue(0, p.nslots);     // W is unchanged until the update: prefetch the next pass now
-  // CD: chain starts from the fresh sample; PCD: from the persistent chain (src/rbm.py:308-311)
-  if (p.pcd) load_chain(); else hidden_from_sums(A0, seg(0, 0), false);
-  mark();   // chain state ready
   // positive-phase means as fp32 for the statistics pass: every CTA converts one slice (published by the
-  // barriers that follow), so that pass does not pay a second sum -> mean round trip
-  {
-    const int per = (BT * p.CQ + (int)gridDim.x - 1) / (int)gridDim.x;
-    for (int i = tid; i < per && cta * per + i < BT * p.CQ; i += NT) {
-      const int e = cta * per + i, b = e / p.CQ, qq = e - b * p.CQ;
-      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B) {
-        const longlong2* sp = reinterpret_cast<const longlong2*>(A0 + b * ldw + 4 * qq);
-        const longlong2 s01 = __ldcg(sp), s23 = __ldcg(sp + 1);
-        const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * qq);
-        m = make_float4(sigmoid_fast_(from_fixed(s01.x) + hb4.x), sigmoid_fast_(from_fixed(s01.y) + hb4.y),
-                        sigmoid_fast_(from_fixed(s23.x) + hb4.z), sigmoid_fast_(from_fixed(s23.y) + hb4.w));
-      }
-      __stcg(reinterpret_cast<float4*>(p.PHf + b * ldw + 4 * qq), m);
-    }
+  // barriers that follow), so that pass does not pay a sum -> mean round trip.  Loads first, the chain
+  // state is rebuilt while they are in flight.
+  const int ph_per = (BT * p.CQ + (int)gridDim.x - 1) / (int)gridDim.x;   // <= NT (plan())
+  const int ph_e = cta * ph_per + tid;
+  const bool ph_mine = tid < ph_per && ph_e < BT * p.CQ;
+  const int ph_b = ph_e / p.CQ, ph_q = ph_e - ph_b * p.CQ;
+  longlong2 ph_s01 = make_longlong2(0, 0), ph_s23 = ph_s01;
+  if (ph_mine && ph_b < B) {
+    const longlong2* sp = reinterpret_cast<const longlong2*>(A0 + ph_b * ldw + 4 * ph_q);
+    ph_s01 = __ldcg(sp);
+    ph_s23 = __ldcg(sp + 1);
   }
+  // CD: chain starts from the fresh sample; PCD: from the persistent chain (src/rbm.py:308-311)
+  if (p.pcd) {
+    load_chain();
+    unsigned long long aux = 0;
+    grid_arrive(p.bar + 2, aux);     // round(v0) sums of this CTA: landed long ago, the fence is free here
+  } else {
+    hidden_from_sums(A0, seg(0, 0), false);
+  }
+  if (ph_mine) {
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ph_b < B) {
+      const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * ph_q);
+      m = make_float4(sigmoid_fast_(from_fixed(ph_s01.x) + hb4.x), sigmoid_fast_(from_fixed(ph_s01.y) + hb4.y),
+                      sigmoid_fast_(from_fixed(ph_s23.x) + hb4.z), sigmoid_fast_(from_fixed(ph_s23.y) + hb4.w));
+    }
+    __stcg(reinterpret_cast<float4*>(p.PHf + ph_b * ldw + 4 * ph_q), m);
+  }
+  mark();   // chain state ready
 
   // pseudo-likelihood monitor (src/rbm.py:421-447), pre-update W, hb, vb: one minibatch row per CTA, taken
   // from the END of the grid (the last CTA owns the fewest rows); its loads overlap the tile prefetch above
-  if (p.pcd) {
-    const int bit = *p.bit_idx;
-    for (int b = (int)gridDim.x - 1 - cta; b < B; b += gridDim.x) {
-      const long long dr = p.idx ? p.idx[b] : b;
-      const float x = roundf(p.data[dr * p.ld_data + bit]);
-      const float d = 1.f - 2.f * x;
-      float h0 = 0.f, h1 = 0.f;
-      for (int j = tid; j < H; j += NT) {
-        const float pre = from_fixed((long long)__ldcg(&A1[b * ldw + j])) + hbs[j];
-        h0 += softplusf_(pre);
-        h1 += softplusf_(pre + d * p.W[(size_t)bit * ldw + j]);
+  if (pl_cta) {
+    const int bit = __float_as_int(misc[60]);
+    const float x = misc[61], d = 1.f - 2.f * x;
+    // W[bit, :] does not depend on the barrier: in flight while thread 0 polls it
+    float wrow[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = tid + u * NT; wrow[u] = j < H ? __ldg(&p.W[(size_t)bit * ldw + j]) : 0.f; }
+    grid_wait(p.bar + 2, gridDim.x);
+    float pre[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = tid + u * NT; pre[u] = j < H ? from_fixed((long long)__ldcg(&A1[pl_b * ldw + j])) + hbs[j] : 0.f; }
+    float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (tid + u * NT < H) {
+        h0 += softplusf_(pre[u]);
+        h1 += softplusf_(pre[u] + d * wrow[u]);
       }
-      h0 = block_sum(h0, misc);
-      h1 = block_sum(h1, misc);
-      if (tid == 0) {
-        const float vbv = p.vb[bit];
-        float vterm;
-        if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
-        else vterm = d * vbv;
-        __stcg(&p.cost_part[b], -(float)V * softplusf_((h1 - h0) + vterm));
-      }
+    }
+    h0 = block_sum(h0, misc);
+    h1 = block_sum(h1, misc);
+    if (tid == 0) {
+      const float vbv = misc[62];
+      float vterm;
+      if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
+      else vterm = d * vbv;
+      __stcg(&p.cost_part[pl_b], -(float)V * softplusf_((h1 - h0) + vterm));
     }
   }
 
@@ -569,7 +631,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
           for (int bx = warp * 2 + half; bx < nbox; bx += NWARP * 2) {
             const unsigned char* bpa = tile + bx * box_bytes + lr * 128;
             const float* hb0 = hs + bx * 32;
-#pragma unroll
+            // NOT fully unrolled: a box is visited once per tile, straight-line code this long is bound by
+            // instruction fetch (ncu: stall_no_instruction); the 2-chunk body is re-run from the i-cache
+#pragma unroll 2
             for (int c = 0; c < 8; ++c) {
               const int sw = (c ^ (lr & 7)) << 4;                                  // rows l and l+16 swizzle alike
               const float4 wa = *reinterpret_cast<const float4*>(bpa + sw);
@@ -687,10 +751,32 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
 #pragma unroll
     for (int b = 0; b < BT; ++b)
       ph[b] = col_ok ? __ldcg(reinterpret_cast<const float4*>(p.PHf + b * ldw + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    means_to_hs(GA(p.k - 1));
+    if constexpr (BT <= 10) {
+      // every thread converts the sums of its own columns: all loads in flight, no shared-memory round
+      const unsigned long long* GL = GA(p.k - 1);
+      longlong2 t[BT][2];
 #pragma unroll
-    for (int b = 0; b < BT; ++b)
-      nh[b] = col_ok ? *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < BT; ++b) {
+        t[b][0] = t[b][1] = make_longlong2(0, 0);
+        if (col_ok && b < B) {
+          const longlong2* sp = reinterpret_cast<const longlong2*>(GL + b * ldw + 4 * q);
+          t[b][0] = __ldcg(sp);
+          t[b][1] = __ldcg(sp + 1);
+        }
+      }
+      const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * (col_ok ? q : 0));
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        nh[b] = (col_ok && b < B)
+                    ? make_float4(sigmoid_fast_(from_fixed(t[b][0].x) + hb4.x), sigmoid_fast_(from_fixed(t[b][0].y) + hb4.y),
+                                  sigmoid_fast_(from_fixed(t[b][1].x) + hb4.z), sigmoid_fast_(from_fixed(t[b][1].y) + hb4.w))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      means_to_hs(GA(p.k - 1));
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        nh[b] = col_ok ? *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int ncol = min(4, H - 4 * q);
     for (int j = 0, stg = 0; j < ntiles_s; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
       wait_stage(stg);
@@ -793,7 +879,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
         *p.bit_idx = (*p.bit_idx + 1) % V;                                 // :445
       } else {
         c = 0.f;
-        for (int i = 0; i < p.n_active; ++i) c += __ldcg(&p.cost_part[i]);
+        for (int i = 0; i < (int)gridDim.x; ++i) c += __ldcg(&p.cost_part[i]);
         c *= p.cost_scale;
       }
       if (p.cost_out) *p.cost_out = c;
@@ -808,6 +894,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     const unsigned long long prev = atomicAdd(p.bar + 1, 1ULL);
     if (prev == gridDim.x - 1) {
       p.bar[0] = 0ULL;
+      p.bar[2] = 0ULL;
       p.bar[1] = 0ULL;
       __threadfence();
     }
@@ -842,7 +929,7 @@ static int make_map(CUtensorMap* tm, const float* W, int V, int ldw, int box_row
 }
 
 struct Geometry {
-  int BT, rows_per_cta, rows_alloc, n_active, CQ, GW, G, R, nbox, nslots, grid, ldh, slot_bytes, ring_bytes;
+  int BT, rows_per_cta, rows_small, n_big, rows_alloc, CQ, GW, G, R, nbox, nslots, grid, ldh, slot_bytes, ring_bytes;
   int off_hs, off_v0, off_nv, off_vt, off_dred, off_bars, off_misc, off_vb, off_hb;
   size_t smem;
   bool ok;
@@ -860,9 +947,19 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   if (g.CQ <= 32) { g.GW = 1; while (g.GW < g.CQ) g.GW <<= 1; } else g.GW = (g.CQ + 31) / 32 * 32;
   g.G = NT / g.GW;
   g.grid = c->num_sms;
+  if (g.BT * g.CQ > g.grid * NT || g.grid < g.BT || a.ldw > 4 * NT) return g;
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
+  g.rows_small = g.rows_per_cta;
+  g.n_big = g.grid;
+  if (a.persistent && a.V >= 8 * g.grid) {
+    // PCD: the last B CTAs also compute the pseudo-likelihood monitor (~2.5 us); they own ~14 % fewer rows
+    g.n_big = g.grid - a.B;
+    g.rows_per_cta = (int)((100LL * a.V + (100LL * g.grid - 14LL * a.B) - 1) / (100LL * g.grid - 14LL * a.B));
+    const int rest = a.V - g.n_big * g.rows_per_cta;
+    g.rows_small = rest > 0 ? (rest + a.B - 1) / a.B : 0;
+    if (g.rows_small > g.rows_per_cta) { g.rows_per_cta = (a.V + g.grid - 1) / g.grid; g.rows_small = g.rows_per_cta; g.n_big = g.grid; }
+  }
   g.rows_alloc = (g.rows_per_cta + 7) & ~7;
-  g.n_active = (a.V + g.rows_per_cta - 1) / g.rows_per_cta;
   g.nbox = (a.ldw + 31) / 32;
   g.ldh = g.nbox * 32;
   // stage = R rows x all columns as nbox swizzled boxes, at most 56 KB
@@ -941,7 +1038,7 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.c2 = (uint32_t)a.rng.offset; p.c3 = (uint32_t)(a.rng.offset >> 32);
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
-  p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.n_active = g.n_active;
+  p.rows_per_cta = g.rows_per_cta; p.rows_small = g.rows_small; p.n_big = g.n_big; p.rows_alloc = g.rows_alloc;
   p.CQ = g.CQ; p.GW = g.GW; p.G = g.G; p.R = g.R; p.nbox = g.nbox; p.nslots = g.nslots;
   p.ldh = g.ldh; p.slot_bytes = g.slot_bytes; p.ring_bytes = g.ring_bytes;
   p.off_hs = g.off_hs; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vt = g.off_vt; p.off_dred = g.off_dred;

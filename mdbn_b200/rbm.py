@@ -102,9 +102,78 @@ class TrainFn:
             return self._call(None, momentum, lr, phase=_lib.PHASE_APPLY, rows_total=rows_total)
         return self.dp.step(indexes, stats_fn, apply_fn)
 
-    def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0):
+    def step_from_host(self, host_batch, momentum=0.0, lr=None, next_host_batch=None, lag=0):
+        """One step on a minibatch that lives in (pinned) HOST memory — the streaming form of the train
+        function for datasets kept off the device.  Two device staging buffers and a copy stream: the
+        host->device copy of `next_host_batch` is enqueued right after this step's kernel and overlaps it.
+        lag=0: the cost of THIS step is read back and returned (same contract as __call__ with sync=True).
+        lag=1: every step's cost is still copied to the host, but the call returns the cost of the PREVIOUS
+        step (None on the first call; `flush()` returns the last one) so that the next step is enqueued
+        before the host blocks — an epoch loop that only averages the costs (src/dbn.py:343-353) is unchanged."""
+        B, V = int(host_batch.shape[0]), int(host_batch.shape[1])
+        st = getattr(self, "_feed", None)
+        if st is None or st["shape"] != (B, V):
+            st = self._feed = {
+                "shape": (B, V), "cur": 0, "staged": [None, None],
+                "buf": [torch.empty((B, V), dtype=torch.float32, device=self.device) for _ in range(2)],
+                "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()],
+                "copy": torch.cuda.Stream(device=self.device),
+                "rows": torch.arange(B, dtype=torch.int32, device=self.device)}
+        main = torch.cuda.current_stream()
+        cur = st["cur"]
+        if st["staged"][cur] is not host_batch:                  # not prefetched by the previous call
+            with torch.cuda.stream(st["copy"]):
+                st["copy"].wait_event(st["free"][cur]) if st["staged"][cur] is not None else None
+                st["buf"][cur].copy_(host_batch, non_blocking=True)
+                st["ready"][cur].record(st["copy"])
+            st["staged"][cur] = host_batch
+        main.wait_event(st["ready"][cur])
+        sync, self.sync = self.sync, False
+        try:
+            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur])
+        finally:
+            self.sync = sync
+        st["free"][cur].record(main)
+        nxt = 1 - cur
+        if next_host_batch is not None:
+            with torch.cuda.stream(st["copy"]):
+                if st["staged"][nxt] is not None:
+                    st["copy"].wait_event(st["free"][nxt])
+                st["buf"][nxt].copy_(next_host_batch, non_blocking=True)
+                st["ready"][nxt].record(st["copy"])
+            st["staged"][nxt] = next_host_batch
+        else:
+            st["staged"][nxt] = None
+        st["cur"] = nxt
+        if not lag:
+            self._cost_host.copy_(self.cost_dev, non_blocking=True)
+            main.synchronize()
+            return float(self._cost_host[0])
+        if "lag" not in st:
+            st["lag"] = {"host": [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                         "ev": [torch.cuda.Event(), torch.cuda.Event()], "n": 0, "pending": None}
+        lg = st["lag"]
+        k = lg["n"] & 1
+        lg["host"][k].copy_(self.cost_dev, non_blocking=True)
+        lg["ev"][k].record(main)
+        prev, lg["pending"], lg["n"] = lg["pending"], k, lg["n"] + 1
+        if prev is None:
+            return None
+        lg["ev"][prev].synchronize()
+        return float(lg["host"][prev][0])
+
+    def flush(self):
+        """Cost of the last lagged step (step_from_host(..., lag=1)); None when nothing is pending."""
+        lg = getattr(self, "_feed", {}).get("lag") if getattr(self, "_feed", None) else None
+        if not lg or lg["pending"] is None:
+            return None
+        k, lg["pending"] = lg["pending"], None
+        lg["ev"][k].synchronize()
+        return float(lg["host"][k][0])
+
+    def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0, data_override=None):
         r, h = self.rbm, self.updates.hyper
-        data = self.data()
+        data = self.data() if data_override is None else data_override
         if indexes is None:                      # APPLY phase: no rows of its own
             idx = torch.zeros(1, dtype=torch.int32, device=self.device)
         elif isinstance(indexes, torch.Tensor):

@@ -15,13 +15,17 @@ class RandomStreams:
     def __init__(self, seed=None):
         self.seed = int(seed) if seed is not None else 12345
         self._site_offsets = {}
+        self._site_ids = {}
 
     def next_rng(self, site, device, n_values=0, **_):
-        """mdbn_rng for the next call of sampling site `site` (an RBM instance / function id)."""
+        """mdbn_rng for the next call of sampling site `site` (an RBM instance / function id).
+        Sites are numbered in order of first use, so a program that makes the same calls in the same order
+        draws the same numbers in every run (the object id itself never enters the stream)."""
+        sid = self._site_ids.setdefault(site, len(self._site_ids))
         off = self._site_offsets.get(site, 0)
         self._site_offsets[site] = off + 1
-        # decorrelate sites by folding the site id into the seed
-        return _lib.Rng(_lib.RNG_PHILOX, None, (self.seed ^ (hash(site) & 0xFFFFFFFF) << 32) & (2 ** 64 - 1), off), None
+        # decorrelate sites by folding the site number into the upper half of the key
+        return _lib.Rng(_lib.RNG_PHILOX, None, (self.seed ^ ((sid * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF) << 32) & (2 ** 64 - 1), off), None
 
 
 class BufferStreams:

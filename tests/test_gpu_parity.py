@@ -469,3 +469,40 @@ def test_stats_apply_phases_equal_full_step(kind, path, tf32, B):
     for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
         a, b = getattr(r_dp, name).get_value(), getattr(r_full, name).get_value()
         close(a, b, rtol=tol, scale=max(np.abs(b).max(), 1e-4), what=name)
+
+
+# ---------------------------------------------------------------------------
+# host-streaming form of the train function: same parameters as the device-resident form
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,pcd", [(O.GRBM, True), (O.RBM, False)])
+def test_step_from_host_equals_device_resident(kind, pcd):
+    m = M()
+    V, H, B, n_mb = 300, 72, 10, 5
+    data = synth(kind, B * n_mb, V, seed=33)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(9), V, H).astype(np.float32)
+
+    def make(dataset):
+        r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(77))
+        P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+        cost, upd = r.get_cost_updates(lr=0.05, k=1, lambda_1=0.01, lambda_2=0.1, batch_size=B, persistent=P)
+        return r, r.make_train_fn(dataset, cost, upd)
+    r_dev, fn_dev = make(data)
+    r_host, fn_host = make(np.zeros((B, V), np.float32))
+    host = [torch.from_numpy(np.ascontiguousarray(data[i * B:(i + 1) * B])).pin_memory() for i in range(n_mb)]
+    for i in range(n_mb):
+        c_dev = fn_dev(np.arange(i * B, (i + 1) * B, dtype=np.int32), 0.5)
+        # odd steps are prefetched by the previous call, even steps are staged on demand
+        nxt = host[i + 1] if (i + 1 < n_mb and i % 2 == 0) else None
+        c_host = fn_host.step_from_host(host[i], 0.5, next_host_batch=nxt)
+        assert c_dev == c_host
+    for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        assert np.array_equal(getattr(r_dev, name).get_value(), getattr(r_host, name).get_value()), name
+    # lag=1: same steps, every cost still reaches the host, one call late
+    r_ref, fn_ref = make(data)
+    r_lag, fn_lag = make(np.zeros((B, V), np.float32))
+    want = [fn_ref(np.arange(i * B, (i + 1) * B, dtype=np.int32), 0.5) for i in range(n_mb)]
+    got = [fn_lag.step_from_host(host[i], 0.5, next_host_batch=host[i + 1] if i + 1 < n_mb else None, lag=1)
+           for i in range(n_mb)]
+    assert got[0] is None and got[1:] == want[:-1] and fn_lag.flush() == want[-1] and fn_lag.flush() is None
+    assert np.array_equal(r_ref.W.get_value(), r_lag.W.get_value())
