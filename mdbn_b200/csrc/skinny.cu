@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     sums_to_hs(src);
     const bool quad_rng = rs.mode != MDBN_RNG_BUFFER && (H & 3) == 0;
     const int n = B * p.CQ;
-#pragma unroll 1
+#pragma unroll 2
     for (int e = tid; e < n; e += NT) {
       const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
       float4* hp = reinterpret_cast<float4*>(hs + b * ldh + j0);
@@ -456,20 +456,6 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
         if (write_p && j0 + t < H) p.P[(size_t)b * H + j0 + t] = sm4[t];
       }
       *hp = make_float4(sm4[0], sm4[1], sm4[2], sm4[3]);
-    }
-    __syncthreads();
-  };
-  // hidden means of a sum buffer into hs (statistics pass: every thread then picks up its own columns)
-  auto means_to_hs = [&](const unsigned long long* src) {
-    sums_to_hs(src);
-    const int n = B * p.CQ;
-#pragma unroll 1
-    for (int e = tid; e < n; e += NT) {
-      const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
-      float4* hp = reinterpret_cast<float4*>(hs + b * ldh + j0);
-      const float4 x = *hp, hb4 = *reinterpret_cast<const float4*>(hbs + j0);
-      *hp = make_float4(sigmoid_fast_(x.x + hb4.x), sigmoid_fast_(x.y + hb4.y), sigmoid_fast_(x.z + hb4.z),
-                        sigmoid_fast_(x.w + hb4.w));
     }
     __syncthreads();
   };
@@ -751,31 +737,33 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
 #pragma unroll
     for (int b = 0; b < BT; ++b)
       ph[b] = col_ok ? __ldcg(reinterpret_cast<const float4*>(p.PHf + b * ldw + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (BT <= 10) {
-      // every thread converts the sums of its own columns: all loads in flight, no shared-memory round
+    {
+      // every thread converts the sums of its own columns, ten rows (20 L2 loads) in flight at a time; no
+      // shared-memory round, no block barrier
       const unsigned long long* GL = GA(p.k - 1);
-      longlong2 t[BT][2];
-#pragma unroll
-      for (int b = 0; b < BT; ++b) {
-        t[b][0] = t[b][1] = make_longlong2(0, 0);
-        if (col_ok && b < B) {
-          const longlong2* sp = reinterpret_cast<const longlong2*>(GL + b * ldw + 4 * q);
-          t[b][0] = __ldcg(sp);
-          t[b][1] = __ldcg(sp + 1);
-        }
-      }
       const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * (col_ok ? q : 0));
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
-        nh[b] = (col_ok && b < B)
-                    ? make_float4(sigmoid_fast_(from_fixed(t[b][0].x) + hb4.x), sigmoid_fast_(from_fixed(t[b][0].y) + hb4.y),
-                                  sigmoid_fast_(from_fixed(t[b][1].x) + hb4.z), sigmoid_fast_(from_fixed(t[b][1].y) + hb4.w))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      means_to_hs(GA(p.k - 1));
+      for (int b0 = 0; b0 < BT; b0 += 10) {
+        longlong2 t[10][2];
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
-        nh[b] = col_ok ? *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 10; ++i) {
+          const int b = b0 + i;
+          t[i][0] = t[i][1] = make_longlong2(0, 0);
+          if (col_ok && b < B) {
+            const longlong2* sp = reinterpret_cast<const longlong2*>(GL + b * ldw + 4 * q);
+            t[i][0] = __ldcg(sp);
+            t[i][1] = __ldcg(sp + 1);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int b = b0 + i;
+          nh[b] = (col_ok && b < B)
+                      ? make_float4(sigmoid_fast_(from_fixed(t[i][0].x) + hb4.x), sigmoid_fast_(from_fixed(t[i][0].y) + hb4.y),
+                                    sigmoid_fast_(from_fixed(t[i][1].x) + hb4.z), sigmoid_fast_(from_fixed(t[i][1].y) + hb4.w))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     }
     const int ncol = min(4, H - 4 * q);
     for (int j = 0, stg = 0; j < ntiles_s; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
