@@ -290,6 +290,28 @@ def main():
         timed(50, True)
     clocks = sampler.stop() if sampler else None
     ms_warm = timed(args.steps, False)                         # same step, single parameter set (L2-warm)
+    # an epoch per launch (TrainFn.run_steps -> mdbn_cd_steps): what DBN.training actually issues.  Parameter
+    # sets still rotate between launches, but inside a launch the layer's 64 MB stay in L2 — reported next
+    # to the headline, never as the headline.
+    chained = None
+    if not tensor and not dp and n_mb >= 2:
+        chain = min(n_mb, 32)
+        idx_mat = perm[: chain * B].view(chain, B)
+        n_l = max(2, args.steps // chain)
+
+        def timed_chained():
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev0.record()
+            for l in range(n_l):
+                fns[l % R].run_steps(idx_mat, w["mom"])
+            ev1.record()
+            barrier()
+            return ev0.elapsed_time(ev1)
+        timed_chained()
+        ms_c = timed_chained() / (n_l * chain)
+        chained = {"steps_per_launch": chain, "ms_per_step": ms_c, "value": world * B / (ms_c * 1e-3),
+                   "note": "one launch per epoch of %d minibatches; weights L2-resident inside a launch" % chain}
     ms_per_step = ms / args.steps
     value = (1 if dp else world) * B / (ms_per_step * 1e-3)
 
@@ -382,6 +404,8 @@ def main():
              "achieved_l2_warm": abytes / (ms_warm / args.steps * 1e-3) / 1e9},
             "value_l2_warm": world * B / (ms_warm / args.steps * 1e-3),
         }
+        if chained is not None:
+            line["epoch_per_launch"] = chained
         if not args.no_cpu_baseline:
             v, cores, n, med = cpu_step_rate(w)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",

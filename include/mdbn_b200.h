@@ -113,6 +113,12 @@ typedef struct {
 
 int mdbn_cd_step(mdbn_ctx* ctx, const mdbn_cd_args* args, void* stream);
 
+/* n_steps consecutive full steps (an epoch, or the minibatches up to the next validation point of
+ * src/dbn.py:343-353): args->indices is [n_steps][B] row-major, args->cost_out [n_steps] (or NULL); step s
+ * draws with rng.offset + s (PHILOX generator only).  Same results as n_steps calls of mdbn_cd_step with
+ * those arguments; on the skinny path it is ONE kernel launch, otherwise a loop of single steps. */
+int mdbn_cd_steps(mdbn_ctx* ctx, const mdbn_cd_args* args, int n_steps, void* stream);
+
 /* size in floats of stats_buf for a layer */
 long long mdbn_stats_size(int V, int H);
 

@@ -176,4 +176,35 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   }
 }
 
+int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream) {
+  MDBN_CHECK(a != nullptr, "cd_steps: args is NULL");
+  MDBN_CHECK(n_steps >= 1, "cd_steps: n_steps must be >= 1");
+  if (n_steps == 1) return mdbn_cd_step(c, a, stream);
+  MDBN_CHECK(a->phase == MDBN_PHASE_FULL, "cd_steps: only full steps can be chained");
+  MDBN_CHECK(a->rng.mode == MDBN_RNG_PHILOX, "cd_steps: the PHILOX generator is required (one offset per step)");
+  MDBN_CHECK(a->indices, "cd_steps: indices [n_steps][B] is required");
+  // one launch when the persistent kernel takes the shape (validation happens in the first single step otherwise)
+  const bool want_skinny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_SKINNY;
+  if (want_skinny && c && a->W && !skinny_tc_supported(c, *a) && skinny_supported(c, *a)) {
+    MDBN_TRY(check_common(c, a->W, a->ldw, a->B, a->V, a->H));
+    MDBN_CHECK(a->kind == MDBN_RBM || a->kind == MDBN_GRBM, "cd_steps: bad kind %d", a->kind);
+    MDBN_CHECK(a->hbias && a->vbias && a->W_speed && a->hbias_speed && a->vbias_speed, "cd_steps: NULL parameter/state");
+    MDBN_CHECK(a->B_nom > 0, "cd_steps: batch_size (B_nom) must be given (src/rbm.py:413)");
+    MDBN_CHECK(a->weightcost == 0.f || a->W_snap, "cd_steps: weightcost != 0 needs W_snap");
+    MDBN_CHECK(a->k >= 1, "cd_steps: k must be >= 1");
+    MDBN_CHECK(a->data && a->ld_data >= a->V, "cd_steps: bad data/ld_data");
+    MDBN_CHECK(!a->persistent || a->bit_i_idx, "cd_steps: PCD needs bit_i_idx");
+    MDBN_CUDA(cudaSetDevice(c->device));
+    return skinny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    mdbn_cd_args one = *a;
+    one.indices = a->indices + (size_t)s * a->B;
+    one.cost_out = a->cost_out ? a->cost_out + s : nullptr;
+    one.rng.offset = a->rng.offset + (unsigned long long)s;
+    MDBN_TRY(mdbn_cd_step(c, &one, stream));
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -78,6 +78,7 @@ int generic_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
 // ---- skinny persistent path (B <= 32): skinny.cu ----------------------------
 bool skinny_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int skinny_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
+int skinny_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t st);
 
 // ---- skinny persistent path on tcgen05 (B <= 16, H <= 512, large layers): skinny_tc.cu
 bool skinny_tc_supported(const mdbn_ctx*, const mdbn_cd_args& a);

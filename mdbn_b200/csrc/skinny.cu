@@ -55,8 +55,9 @@ struct Params {
   // global scratch: fixed-point (2^-32) accumulators of the hidden pre-activation sums, [5][BT][ldw]:
   // 0 = positive phase, 1 = round(v0) (pseudo-likelihood), 2..4 = Gibbs steps (rotating).  Zero on entry;
   // `acc_other` is the set of the previous launch, cleared by this one.
-  unsigned long long *acc, *acc_other;
+  unsigned long long *acc, *acc_other;   // set of step 0 / the other one; they alternate from step to step
   int n_acc;          // BT * ldw
+  int n_steps;        // minibatches processed by this launch (idx [n_steps][B], cost_out [n_steps])
   float* cost_part;   // [max(gridDim, BT)]
   float* PHf;         // [BT][ldw] positive-phase hidden means as fp32 (written in slices after barrier 0)
   unsigned long long* bar;   // [0] barrier counter, [1] exit counter
@@ -187,8 +188,11 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   uint32_t phase_bits = 0;
   int dbg_i = 0;
   const int F = p.dbg_flags;
+  int step = 0;                                  // minibatch of this launch being processed
+  const int* idxp = p.idx;                       // its row numbers
+  uint32_t c2s = p.c2, c3s = p.c3;               // its Philox offset (rng.offset + step)
   auto mark = [&]() {
-    if (p.dbg && cta == 0 && tid == 0) {
+    if (p.dbg && cta == 0 && tid == 0 && step == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       p.dbg[dbg_i++] = t;
@@ -201,9 +205,6 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int e = tid; e < BT * ldh; e += NT) hs[e] = 0.f;
-  for (int j = tid; j < ldh; j += NT) hbs[j] = j < H ? p.hb[j] : 0.f;
-  // clear the accumulator set of the previous launch (nobody touches it during this one)
-  for (int i = cta * NT + tid; i < 5 * p.n_acc; i += gridDim.x * NT) __stcg(&p.acc_other[i], 0ULL);
   __syncthreads();
 
   // ---- tile pipeline --------------------------------------------------------------
@@ -252,54 +253,9 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     RngSeg s;
     s.mode = p.rng_mode;
     s.seg = p.ubuf ? p.ubuf + off : nullptr;
-    s.k0 = p.k0; s.k1 = p.k1; s.c1 = ordinal; s.c2 = p.c2; s.c3 = p.c3;
+    s.k0 = p.k0; s.k1 = p.k1; s.c1 = ordinal; s.c2 = c2s; s.c3 = c3s;
     return s;
   };
-
-  // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
-  if (!(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
-  for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
-  // the minibatch row numbers first (one dependent load for everybody), then eight gathers in flight per thread
-  int* sidx = reinterpret_cast<int*>(misc) + 32;
-  if (tid < BTS) sidx[tid] = tid < B ? (p.idx ? p.idx[tid] : tid) : -1;
-  // pseudo-likelihood monitor: the CTA that will compute it for minibatch row pl_b fetches its scalars now
-  // (three dependent loads that would otherwise sit on that CTA's critical path)
-  const int pl_b = (int)gridDim.x - 1 - cta;
-  const bool pl_cta = p.pcd && pl_b < B;
-  if (pl_cta && tid == NT - 1) {
-    const int bit = *p.bit_idx;
-    const long long dr = p.idx ? p.idx[pl_b] : pl_b;
-    misc[60] = __int_as_float(bit);
-    misc[61] = roundf(p.data[dr * p.ld_data + bit]);
-    misc[62] = p.vb[bit];
-  }
-  __syncthreads();
-  {
-    constexpr int UG = 8;
-    const int n = p.rows_alloc * BTS;
-    for (int e0 = tid; e0 < n; e0 += UG * NT) {
-      float x[UG];
-#pragma unroll
-      for (int u = 0; u < UG; ++u) {
-        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
-        x[u] = 0.f;
-        if (e < n && r < rows) {
-          const int dr = sidx[b];
-          if (dr >= 0) x[u] = __ldg(&p.data[(long long)dr * p.ld_data + row0 + r]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UG; ++u) {
-        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
-        if (e < n) {
-          v0s[r * BTS + b] = x[u];
-          nvs[r * BTS + b] = p.pcd ? roundf(x[u]) : 0.f;   // src/rbm.py:428; the nv slab is free until the last Gibbs step
-        }
-      }
-    }
-  }
-  __syncthreads();
-  mark();   // gather done
 
   // ---- propup of one staged tile: acc[b][4q..4q+3] += src[r][b] * W[r, 4q..4q+3]; DUAL shares the W loads.
   //      Packed FFMA2: an accumulator pair is (row b, row b+1) of one column, the v pair comes straight out
@@ -489,9 +445,70 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     }
     __syncthreads();
   };
-  unsigned long long* const A0 = p.acc;
-  unsigned long long* const A1 = p.acc + p.n_acc;
-  auto GA = [&](int s) { return p.acc + (size_t)(2 + s % 3) * p.n_acc; };
+
+  // the pseudo-likelihood bit index advances by one per step (src/rbm.py:445): read once, written once
+  const int pl_b = (int)gridDim.x - 1 - cta;
+  const bool pl_cta = p.pcd && pl_b < B;
+  const int bit0 = (p.pcd && (cta == 0 || pl_cta)) ? *p.bit_idx : 0;
+
+  // ======================= one CD-k / PCD-k step per iteration =======================
+  // Steps of one launch need no extra synchronisation: a CTA only ever reads ITS rows of W, W_speed and vb;
+  // what crosses CTAs (hidden bias, persistent chain, accumulators, cost partials) is written after the last
+  // barrier of step s and read after the first barrier of step s+1.
+  for (step = 0; step < p.n_steps; ++step) {
+  idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
+  {
+    const unsigned long long off64 = (((unsigned long long)p.c3 << 32) | p.c2) + (unsigned long long)step;
+    c2s = (uint32_t)off64; c3s = (uint32_t)(off64 >> 32);
+  }
+  unsigned long long* const accp = (step & 1) ? p.acc_other : p.acc;
+  unsigned long long* const acc_prev = (step & 1) ? p.acc : p.acc_other;
+  unsigned long long* const A0 = accp;
+  unsigned long long* const A1 = accp + p.n_acc;
+  auto GA = [&](int s) { return accp + (size_t)(2 + s % 3) * p.n_acc; };
+
+  // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
+  if (!(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
+  for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? __ldcg(&p.vb[row0 + r]) : 0.f;
+  // the minibatch row numbers first (one dependent load for everybody), then eight gathers in flight per thread
+  int* sidx = reinterpret_cast<int*>(misc) + 32;
+  if (tid < BTS) sidx[tid] = tid < B ? (idxp ? idxp[tid] : tid) : -1;
+  // pseudo-likelihood monitor: the CTA that will compute it for minibatch row pl_b fetches its scalars now
+  // (three dependent loads that would otherwise sit on that CTA's critical path)
+  if (pl_cta && tid == NT - 1) {
+    const int bit = (bit0 + step) % V;                                 // src/rbm.py:445, one advance per step
+    const long long dr = idxp ? idxp[pl_b] : pl_b;
+    misc[60] = __int_as_float(bit);
+    misc[61] = roundf(p.data[dr * p.ld_data + bit]);
+    misc[62] = __ldcg(&p.vb[bit]);
+  }
+  __syncthreads();
+  {
+    constexpr int UG = 8;
+    const int n = p.rows_alloc * BTS;
+    for (int e0 = tid; e0 < n; e0 += UG * NT) {
+      float x[UG];
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
+        x[u] = 0.f;
+        if (e < n && r < rows) {
+          const int dr = sidx[b];
+          if (dr >= 0) x[u] = __ldg(&p.data[(long long)dr * p.ld_data + row0 + r]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        const int e = e0 + u * NT, b = e / p.rows_alloc, r = e - b * p.rows_alloc;
+        if (e < n) {
+          v0s[r * BTS + b] = x[u];
+          nvs[r * BTS + b] = p.pcd ? roundf(x[u]) : 0.f;   // src/rbm.py:428; the nv slab is free until the last Gibbs step
+        }
+      }
+    }
+  }
+  __syncthreads();
+  mark();   // gather done
 
   // =============================== pass 0: positive phase ===============================
   {
@@ -521,6 +538,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   grid_wait(p.bar, bar_target);
   mark();
   if (!(F & 32)) issue(0, p.nslots);     // W is unchanged until the update: prefetch the next pass now
+  // every CTA is past the previous step now: the hidden bias it wrote is final, and nobody reads the
+  // accumulator set of the previous step (or launch) any more -> clear it for the next one
+  for (int j = tid; j < ldh; j += NT) hbs[j] = j < H ? __ldcg(&p.hb[j]) : 0.f;
+  for (int i = cta * NT + tid; i < 5 * p.n_acc; i += gridDim.x * NT) __stcg(&acc_prev[i], 0ULL);
   // positive-phase means as fp32 for the statistics pass: every CTA converts one slice (published by the
   // barriers that follow), so that pass does not pay a sum -> mean round trip.  Loads first, the chain
   // state is rebuilt while they are in flight.
@@ -561,8 +582,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     // W[bit, :] does not depend on the barrier: in flight while thread 0 polls it
     float wrow[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int j = tid + u * NT; wrow[u] = j < H ? __ldg(&p.W[(size_t)bit * ldw + j]) : 0.f; }
-    grid_wait(p.bar + 2, gridDim.x);
+    for (int u = 0; u < 4; ++u) { const int j = tid + u * NT; wrow[u] = j < H ? __ldcg(&p.W[(size_t)bit * ldw + j]) : 0.f; }
+    grid_wait(p.bar + 2, (unsigned long long)(step + 1) * gridDim.x);
     float pre[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const int j = tid + u * NT; pre[u] = j < H ? from_fixed((long long)__ldcg(&A1[pl_b * ldw + j])) + hbs[j] : 0.f; }
@@ -835,7 +856,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
       for (int b = 0; b < B; ++b) gsum += v0s[r * BTS + b] - nvs[r * BTS + b];
       float gb = gsum * p.inv_b, sv = p.Svb[row0 + r];
       p.Svb[row0 + r] = gb + (sv - gb) * p.mom;
-      p.vb[row0 + r] = p.vb[row0 + r] + sv * p.lr;
+      p.vb[row0 + r] = vbs[r] + sv * p.lr;
     }
     // hidden bias  src/rbm.py:416 — one CTA (the last: it owns the fewest rows), from the means already in
     // the registers of row group 0
@@ -864,17 +885,22 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
         c = 0.f;
         for (int b = 0; b < B; ++b) c += __ldcg(&p.cost_part[b]);
         c *= p.cost_scale;
-        *p.bit_idx = (*p.bit_idx + 1) % V;                                 // :445
+        if (step == p.n_steps - 1) *p.bit_idx = (bit0 + p.n_steps) % V;     // :445
       } else {
         c = 0.f;
         for (int i = 0; i < (int)gridDim.x; ++i) c += __ldcg(&p.cost_part[i]);
         c *= p.cost_scale;
       }
-      if (p.cost_out) *p.cost_out = c;
+      if (p.cost_out) p.cost_out[step] = c;
     }
   }
 
   mark();   // stats + update done
+  // the rows this CTA just wrote with ordinary stores are read by TMA (async proxy) in the next step
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  }   // step
+
   // reset the barrier for the next launch: the last CTA out switches off the lights
   __syncthreads();
   if (tid == 0) {
@@ -1004,8 +1030,14 @@ bool skinny_supported(const mdbn_ctx* c, const mdbn_cd_args& a) {
   return sk::plan(c, a).ok;
 }
 
-int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
+int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) { return skinny_cd_steps(c, a, 1, st); }
+
+// n_steps consecutive steps in ONE launch: a.indices is [n_steps][B], a.cost_out [n_steps], step s draws with
+// rng.offset + s (PHILOX only).  Same results as n_steps single-step calls.
+int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t st) {
   sk::Geometry g = sk::plan(c, a);
+  MDBN_CHECK(n_steps >= 1, "skinny path: n_steps must be >= 1");
+  MDBN_CHECK(n_steps == 1 || a.rng.mode == MDBN_RNG_PHILOX, "skinny path: multi-step launches need the PHILOX generator");
   MDBN_CHECK(g.ok, "skinny path: unsupported shape");
   sk::Params p{};
   p.W = a.W; p.S = a.W_speed; p.Wsnap = a.weightcost != 0.f ? a.W_snap : nullptr; p.ldw = a.ldw;
@@ -1051,7 +1083,8 @@ int skinny_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   p.n_acc = (int)n_acc;
   p.acc = base + (size_t)c->skinny_parity * 5 * n_acc;
   p.acc_other = base + (size_t)(1 - c->skinny_parity) * 5 * n_acc;
-  c->skinny_parity ^= 1u;
+  c->skinny_parity = (c->skinny_parity + (unsigned)n_steps) & 1u;
+  p.n_steps = n_steps;
   p.cost_part = reinterpret_cast<float*>(base + 2 * 5 * n_acc);
   p.PHf = p.cost_part + g.grid + 64;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);

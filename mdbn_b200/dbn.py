@@ -143,13 +143,25 @@ class DBN(object):
                 flat = torch.as_tensor(numpy.concatenate(minibatches)).to(self.device)   # one H2D per epoch
                 if not isinstance(self.rbm_layers[i], GRBM) and epoch == 6:
                     momentum = 0.9                                                                # :452-453
-                lo = 0
-                for mb, minibatch in enumerate(minibatches):
-                    cost_dev = fn(indexes=flat[lo:lo + len(minibatch)], momentum=momentum, lr=pretrain_lr[i])
-                    lo += len(minibatch)
-                    iter = (epoch - 1) * n_train_batches + mb
+                lo, mb = 0, 0
+                while mb < len(minibatches):
+                    # Chain the minibatches up to the next iteration at which the reference's loop looks at
+                    # anything: a validation iteration, or the one where the patience runs out (patience only
+                    # changes on validation iterations, so it is constant inside a chunk).  Same steps, same
+                    # order; with the in-kernel generator one launch per chunk (TrainFn.run_steps).
+                    iter0 = (epoch - 1) * n_train_batches + mb
+                    B0 = len(minibatches[mb])
+                    next_val = (iter0 // validation_frequency + 1) * validation_frequency - 1
+                    stop = min(next_val, max(patience, iter0), (epoch - 1) * n_train_batches + len(minibatches) - 1)
+                    n = 1
+                    while n < stop - iter0 + 1 and len(minibatches[mb + n]) == B0:
+                        n += 1
+                    costs_dev = fn.run_steps(flat[lo:lo + n * B0].view(n, B0), momentum=momentum, lr=pretrain_lr[i])
+                    lo += n * B0
+                    mb += n
+                    iter = iter0 + n - 1
                     if (iter + 1) % validation_frequency == 0:
-                        current_cost = float(cost_dev.item())
+                        current_cost = float(costs_dev[n - 1].item())
                         log('Pre-training cost (layer %i, epoch %d): ' % (i, epoch), end=' ')
                         log(current_cost)
                         feg = None

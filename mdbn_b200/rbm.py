@@ -171,7 +171,34 @@ class TrainFn:
         lg["ev"][k].synchronize()
         return float(lg["host"][k][0])
 
-    def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0, data_override=None):
+    def run_steps(self, index_matrix, momentum=0.0, lr=None):
+        """`n` consecutive steps from an [n, B] matrix of row numbers — an epoch, or the minibatches up to the
+        next validation point (src/dbn.py:343-353).  Same parameters, chains and costs as n single calls;
+        with the in-kernel generator on the skinny path it is ONE kernel launch (mdbn_cd_steps).
+        Returns the n costs: a device tensor when sync is False, else a list of floats."""
+        if isinstance(index_matrix, torch.Tensor):
+            idx = index_matrix.to(device=self.device, dtype=torch.int32)
+        else:
+            idx = torch.as_tensor(numpy.asarray(index_matrix, dtype=numpy.int32)).to(self.device)
+        idx = idx.reshape(1, -1) if idx.dim() == 1 else idx.contiguous()
+        n = int(idx.shape[0])
+        chained = (n > 1 and getattr(self.rbm.theano_rng, "mode", None) == _lib.RNG_PHILOX
+                   and not (self.dp is not None and self.dp.world > 1))
+        if chained:
+            costs = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._call(idx, momentum, lr, n_steps=n, costs=costs)
+        else:
+            sync, self.sync = self.sync, False
+            try:
+                costs = torch.stack([self(idx[s], momentum, lr).reshape(()).clone() for s in range(n)])
+            finally:
+                self.sync = sync
+        if not self.sync:
+            return costs
+        return [float(c) for c in costs.cpu()]
+
+    def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0, data_override=None,
+              n_steps=1, costs=None):
         r, h = self.rbm, self.updates.hyper
         data = self.data() if data_override is None else data_override
         if indexes is None:                      # APPLY phase: no rows of its own
@@ -180,7 +207,7 @@ class TrainFn:
             idx = indexes.to(device=self.device, dtype=torch.int32)
         else:
             idx = torch.as_tensor(numpy.asarray(indexes, dtype=numpy.int32)).to(self.device)
-        B = int(idx.numel())
+        B = int(idx.numel()) // int(n_steps)
         persistent = h.get("persistent")
         if persistent is not None and persistent.shape[0] != B and phase != _lib.PHASE_APPLY:
             raise ValueError("PCD chain has %d rows but the minibatch has %d (the reference fails the same way)"
@@ -190,7 +217,7 @@ class TrainFn:
         if phase == _lib.PHASE_APPLY:
             rng, keep = _lib.Rng(_lib.RNG_PHILOX, None, 0, 0), None
         else:
-            rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B)
+            rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B, n_steps=n_steps)
         a = _lib.CdArgs()
         a.kind, a.noisy = r.kind, int(not getattr(r, "error_free", True))
         a.B, a.B_nom, a.V, a.H, a.k = B, int(h["batch_size"]), r.n_visible, r.n_hidden, int(h["k"])
@@ -207,19 +234,24 @@ class TrainFn:
         a.momentum = float(momentum)
         a.lambda_1, a.lambda_2, a.weightcost = float(h["lambda_1"]), float(h["lambda_2"]), float(h["weightcost"])
         a.rng = rng
-        a.cost_out = self.cost_dev.data_ptr()
+        a.cost_out = self.cost_dev.data_ptr() if costs is None else costs.data_ptr()
         a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), phase
         if phase != _lib.PHASE_FULL:
             a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
             if a.path == _lib.PATH_SKINNY or phase == _lib.PHASE_APPLY:
                 a.path = _lib.PATH_AUTO      # the update from reduced statistics is one elementwise kernel
-        _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
-        self._keep = (keep, idx, data)
-        self.n_calls += 1
+        if n_steps > 1:
+            _lib.check(r.ctx.lib.mdbn_cd_steps(r.ctx.handle, ctypes.byref(a), int(n_steps), _stream()))
+        else:
+            _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
+        self._keep = (keep, idx, data, costs)
+        self.n_calls += int(n_steps)
         if phase == _lib.PHASE_STATS:
             return None
         for s in (r.W, r.hbias, r.vbias):
             s.version += 1
+        if costs is not None:
+            return costs
         if not self.sync:
             return self.cost_dev
         self._cost_host.copy_(self.cost_dev, non_blocking=True)

@@ -17,13 +17,13 @@ class RandomStreams:
         self._site_offsets = {}
         self._site_ids = {}
 
-    def next_rng(self, site, device, n_values=0, **_):
-        """mdbn_rng for the next call of sampling site `site` (an RBM instance / function id).
+    def next_rng(self, site, device, n_values=0, n_steps=1, **_):
+        """mdbn_rng for the next call (or the next `n_steps` chained calls) of sampling site `site`.
         Sites are numbered in order of first use, so a program that makes the same calls in the same order
         draws the same numbers in every run (the object id itself never enters the stream)."""
         sid = self._site_ids.setdefault(site, len(self._site_ids))
         off = self._site_offsets.get(site, 0)
-        self._site_offsets[site] = off + 1
+        self._site_offsets[site] = off + int(n_steps)
         # decorrelate sites by folding the site number into the upper half of the key
         return _lib.Rng(_lib.RNG_PHILOX, None, (self.seed ^ ((sid * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF) << 32) & (2 ** 64 - 1), off), None
 

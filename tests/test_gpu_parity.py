@@ -506,3 +506,34 @@ def test_step_from_host_equals_device_resident(kind, pcd):
            for i in range(n_mb)]
     assert got[0] is None and got[1:] == want[:-1] and fn_lag.flush() == want[-1] and fn_lag.flush() is None
     assert np.array_equal(r_ref.W.get_value(), r_lag.W.get_value())
+
+
+# ---------------------------------------------------------------------------
+# chained steps (mdbn_cd_steps / TrainFn.run_steps): one launch == n single-step launches
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,pcd,V,H,B", [(O.GRBM, True, 2000, 72, 10), (O.RBM, False, 300, 100, 20),
+                                            (O.GRBM, False, 19937, 400, 10), (O.RBM, True, 500, 64, 64)])
+def test_run_steps_equals_single_steps(kind, pcd, V, H, B):
+    m = M()
+    n = 5
+    data = synth(kind, B * n, V, seed=41)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(3), V, H).astype(np.float32)
+
+    def make():
+        r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(5))
+        P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+        cost, upd = r.get_cost_updates(lr=0.02, k=1, lambda_1=0.01, lambda_2=0.1, batch_size=B, persistent=P)
+        return r, r.make_train_fn(data, cost, upd), P
+    idx = np.random.RandomState(1).permutation(B * n).astype(np.int32).reshape(n, B)
+    r1, f1, P1 = make()
+    single = [f1(idx[s], 0.5) for s in range(n)] + [f1(idx[0], 0.5)]
+    r2, f2, P2 = make()
+    chained = f2.run_steps(idx, 0.5) + [f2(idx[0], 0.5)]        # a single step after the chain continues the same streams
+    assert f1.n_calls == f2.n_calls == n + 1
+    assert single == chained
+    for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        assert np.array_equal(getattr(r1, name).get_value(), getattr(r2, name).get_value()), name
+    if pcd:
+        assert np.array_equal(P1.get_value(), P2.get_value())
+        assert int(r1.bit_i_idx.item()) == int(r2.bit_i_idx.item()) == (n + 1) % V
