@@ -111,6 +111,10 @@ typedef struct {
   int B_total;           /* APPLY: rows summed over all ranks (bias means, cost mean) */
 } mdbn_cd_args;
 
+/* Staging helper of the host-streaming train step (TrainFn.step_from_host): cudaMemcpyAsync(cudaMemcpyDefault)
+ * on `stream`; host buffers should be pinned. */
+int mdbn_copy_async(void* dst, const void* src, unsigned long long bytes, void* stream);
+
 int mdbn_cd_step(mdbn_ctx* ctx, const mdbn_cd_args* args, void* stream);
 
 /* n_steps consecutive full steps (an epoch, or the minibatches up to the next validation point of

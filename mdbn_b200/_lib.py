@@ -41,7 +41,7 @@ class CdArgs(C.Structure):
 
 EXPORTS = ("mdbn_abi_version", "mdbn_last_error", "mdbn_create", "mdbn_destroy", "mdbn_launch_count",
            "mdbn_set_tf32_phases",
-           "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_stats_size")
+           "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_copy_async", "mdbn_stats_size")
 
 _lib = None
 _lock = threading.Lock()
@@ -74,6 +74,7 @@ def load():
         lib.mdbn_free_energy.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, i, i, vp, vp]
         lib.mdbn_cd_step.argtypes = [vp, C.POINTER(CdArgs), vp]
         lib.mdbn_cd_steps.argtypes = [vp, C.POINTER(CdArgs), C.c_int, vp]
+        lib.mdbn_copy_async.argtypes = [vp, vp, C.c_ulonglong, vp]
         for n in EXPORTS:
             getattr(lib, n)
         if lib.mdbn_abi_version() != 1:

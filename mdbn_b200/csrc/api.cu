@@ -76,6 +76,12 @@ int mdbn_destroy(mdbn_ctx* c) {
 
 unsigned long long mdbn_launch_count(const mdbn_ctx* c) { return c ? c->launches : 0; }
 
+int mdbn_copy_async(void* dst, const void* src, unsigned long long bytes, void* stream) {
+  MDBN_CHECK(dst && src, "copy_async: NULL pointer");
+  MDBN_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
 int mdbn_set_tf32_phases(mdbn_ctx* c, int enable) {
   MDBN_CHECK(c != nullptr, "ctx is NULL");
   c->tf32_phases = enable != 0;

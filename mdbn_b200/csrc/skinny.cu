@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     const long long dr = idxp ? idxp[pl_b] : pl_b;
     misc[60] = __int_as_float(bit);
     misc[61] = roundf(p.data[dr * p.ld_data + bit]);
-    misc[62] = __ldcg(&p.vb[bit]);
+    // (vb[bit] belongs to another CTA, which may still be updating it for the previous step of this launch:
+    //  it is read after the first barrier of the step, below)
   }
   __syncthreads();
   {
@@ -579,6 +580,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   if (pl_cta) {
     const int bit = __float_as_int(misc[60]);
     const float x = misc[61], d = 1.f - 2.f * x;
+    const float vbv = tid == 0 ? __ldcg(&p.vb[bit]) : 0.f;
     // W[bit, :] does not depend on the barrier: in flight while thread 0 polls it
     float wrow[4];
 #pragma unroll
@@ -598,7 +600,6 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     h0 = block_sum(h0, misc);
     h1 = block_sum(h1, misc);
     if (tid == 0) {
-      const float vbv = misc[62];
       float vterm;
       if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
       else vterm = d * vbv;

@@ -113,40 +113,44 @@ class TrainFn:
         B, V = int(host_batch.shape[0]), int(host_batch.shape[1])
         st = getattr(self, "_feed", None)
         if st is None or st["shape"] != (B, V):
+            main = torch.cuda.current_stream()       # looked up once: torch.cuda.current_stream() costs ~13 us
+            copy = torch.cuda.Stream(device=self.device)
             st = self._feed = {
-                "shape": (B, V), "cur": 0, "staged": [None, None],
+                "shape": (B, V), "cur": 0, "staged": [None, None], "nbytes": B * V * 4,
                 "buf": [torch.empty((B, V), dtype=torch.float32, device=self.device) for _ in range(2)],
                 "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()],
-                "copy": torch.cuda.Stream(device=self.device),
+                "copy": copy, "copy_h": ctypes.c_void_p(copy.cuda_stream),
+                "main": main, "main_h": ctypes.c_void_p(main.cuda_stream),
                 "rows": torch.arange(B, dtype=torch.int32, device=self.device)}
-        main = torch.cuda.current_stream()
+        lib = self.rbm.ctx.lib
+        main, copy = st["main"], st["copy"]
+
+        def stage(slot, batch):
+            if batch.dtype != torch.float32 or not batch.is_contiguous():
+                raise TypeError("step_from_host takes contiguous float32 [B, V] host tensors (pinned for overlap)")
+            if st["staged"][slot] is not None:
+                copy.wait_event(st["free"][slot])
+            _lib.check(lib.mdbn_copy_async(st["buf"][slot].data_ptr(), batch.data_ptr(), st["nbytes"], st["copy_h"]))
+            st["ready"][slot].record(copy)
+            st["staged"][slot] = batch
         cur = st["cur"]
         if st["staged"][cur] is not host_batch:                  # not prefetched by the previous call
-            with torch.cuda.stream(st["copy"]):
-                st["copy"].wait_event(st["free"][cur]) if st["staged"][cur] is not None else None
-                st["buf"][cur].copy_(host_batch, non_blocking=True)
-                st["ready"][cur].record(st["copy"])
-            st["staged"][cur] = host_batch
+            stage(cur, host_batch)
         main.wait_event(st["ready"][cur])
         sync, self.sync = self.sync, False
         try:
-            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur])
+            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur], stream=st["main_h"])
         finally:
             self.sync = sync
         st["free"][cur].record(main)
         nxt = 1 - cur
         if next_host_batch is not None:
-            with torch.cuda.stream(st["copy"]):
-                if st["staged"][nxt] is not None:
-                    st["copy"].wait_event(st["free"][nxt])
-                st["buf"][nxt].copy_(next_host_batch, non_blocking=True)
-                st["ready"][nxt].record(st["copy"])
-            st["staged"][nxt] = next_host_batch
+            stage(nxt, next_host_batch)
         else:
             st["staged"][nxt] = None
         st["cur"] = nxt
         if not lag:
-            self._cost_host.copy_(self.cost_dev, non_blocking=True)
+            _lib.check(lib.mdbn_copy_async(self._cost_host.data_ptr(), self.cost_dev.data_ptr(), 4, st["main_h"]))
             main.synchronize()
             return float(self._cost_host[0])
         if "lag" not in st:
@@ -154,7 +158,7 @@ class TrainFn:
                          "ev": [torch.cuda.Event(), torch.cuda.Event()], "n": 0, "pending": None}
         lg = st["lag"]
         k = lg["n"] & 1
-        lg["host"][k].copy_(self.cost_dev, non_blocking=True)
+        _lib.check(lib.mdbn_copy_async(lg["host"][k].data_ptr(), self.cost_dev.data_ptr(), 4, st["main_h"]))
         lg["ev"][k].record(main)
         prev, lg["pending"], lg["n"] = lg["pending"], k, lg["n"] + 1
         if prev is None:
@@ -198,7 +202,7 @@ class TrainFn:
         return [float(c) for c in costs.cpu()]
 
     def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0, data_override=None,
-              n_steps=1, costs=None):
+              n_steps=1, costs=None, stream=None):
         r, h = self.rbm, self.updates.hyper
         data = self.data() if data_override is None else data_override
         if indexes is None:                      # APPLY phase: no rows of its own
@@ -240,10 +244,11 @@ class TrainFn:
             a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
             if a.path == _lib.PATH_SKINNY or phase == _lib.PHASE_APPLY:
                 a.path = _lib.PATH_AUTO      # the update from reduced statistics is one elementwise kernel
+        stream = _stream() if stream is None else stream
         if n_steps > 1:
-            _lib.check(r.ctx.lib.mdbn_cd_steps(r.ctx.handle, ctypes.byref(a), int(n_steps), _stream()))
+            _lib.check(r.ctx.lib.mdbn_cd_steps(r.ctx.handle, ctypes.byref(a), int(n_steps), stream))
         else:
-            _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), _stream()))
+            _lib.check(r.ctx.lib.mdbn_cd_step(r.ctx.handle, ctypes.byref(a), stream))
         self._keep = (keep, idx, data, costs)
         self.n_calls += int(n_steps)
         if phase == _lib.PHASE_STATS:
@@ -444,11 +449,14 @@ class RBM(object):
             # one H2D copy of the whole epoch's index list instead of one per step
             flat = torch.as_tensor(numpy.concatenate(minibatches)).to(self.device)
             costs = torch.empty(len(minibatches), dtype=torch.float32, device=self.device)
-            lo = 0
-            for i, mb in enumerate(minibatches):
-                c = train_rbm(flat[lo:lo + len(mb)], momentum)
-                costs[i:i + 1].copy_(c)
-                lo += len(mb)
+            lo, i = 0, 0
+            while i < len(minibatches):          # runs of equal-length minibatches: one chained launch each
+                B0, n = len(minibatches[i]), 1
+                while i + n < len(minibatches) and len(minibatches[i + n]) == B0:
+                    n += 1
+                costs[i:i + n].copy_(train_rbm.run_steps(flat[lo:lo + n * B0].view(n, B0), momentum))
+                lo += n * B0
+                i += n
             feg = float(self.free_energy_gap(train[:n_val], val))             # :597, :549-558
             mean_cost = float(costs.double().mean())
             history.append((mean_cost, feg))
