@@ -137,9 +137,22 @@ class TrainFn:
         if st["staged"][cur] is not host_batch:                  # not prefetched by the previous call
             stage(cur, host_batch)
         main.wait_event(st["ready"][cur])
+        # the cost of step n goes to slot n%2 of a small device ring and is read back on a THIRD stream: a
+        # 4-byte D2H copy in the main stream would sit between two kernels (~10 us per step)
+        if "lag" not in st:
+            d2h = torch.cuda.Stream(device=self.device)
+            st["lag"] = {"host": [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                         "dev": torch.zeros(2, dtype=torch.float32, device=self.device),
+                         "ev": [torch.cuda.Event(), torch.cuda.Event()], "n": 0, "pending": None,
+                         "d2h": d2h, "d2h_h": ctypes.c_void_p(d2h.cuda_stream)}
+        lg = st["lag"]
+        k = lg["n"] & 1
+        if lg["n"] >= 2:
+            main.wait_event(lg["ev"][k])         # slot k was read back two steps ago (long done)
         sync, self.sync = self.sync, False
         try:
-            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur], stream=st["main_h"])
+            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur], stream=st["main_h"],
+                       costs=lg["dev"][k:k + 1])
         finally:
             self.sync = sync
         st["free"][cur].record(main)
@@ -149,18 +162,15 @@ class TrainFn:
         else:
             st["staged"][nxt] = None
         st["cur"] = nxt
+        lg["d2h"].wait_event(st["free"][cur])
+        _lib.check(lib.mdbn_copy_async(lg["host"][k].data_ptr(), lg["dev"].data_ptr() + 4 * k, 4, lg["d2h_h"]))
+        lg["ev"][k].record(lg["d2h"])
+        prev, lg["n"] = lg["pending"], lg["n"] + 1
         if not lag:
-            _lib.check(lib.mdbn_copy_async(self._cost_host.data_ptr(), self.cost_dev.data_ptr(), 4, st["main_h"]))
-            main.synchronize()
-            return float(self._cost_host[0])
-        if "lag" not in st:
-            st["lag"] = {"host": [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
-                         "ev": [torch.cuda.Event(), torch.cuda.Event()], "n": 0, "pending": None}
-        lg = st["lag"]
-        k = lg["n"] & 1
-        _lib.check(lib.mdbn_copy_async(lg["host"][k].data_ptr(), self.cost_dev.data_ptr(), 4, st["main_h"]))
-        lg["ev"][k].record(main)
-        prev, lg["pending"], lg["n"] = lg["pending"], k, lg["n"] + 1
+            lg["pending"] = None
+            lg["ev"][k].synchronize()
+            return float(lg["host"][k][0])
+        lg["pending"] = k
         if prev is None:
             return None
         lg["ev"][prev].synchronize()
