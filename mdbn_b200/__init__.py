@@ -7,6 +7,7 @@ from .rbm import RBM, GRBM
 from .mlp import HiddenLayer
 from .dbn import DBN
 from . import MDBN
+from . import io
 
-__all__ = ["RBM", "GRBM", "DBN", "HiddenLayer", "MDBN", "Shared", "shared", "get_minibatches_idx",
+__all__ = ["RBM", "GRBM", "DBN", "HiddenLayer", "MDBN", "io", "Shared", "shared", "get_minibatches_idx",
            "RandomStreams", "BufferStreams"]

@@ -304,7 +304,79 @@ def mdbn_case(name, seed=5):
     print("wrote", name)
 
 
+
+def io_case():
+    """the table loader / pre-processing before the path, the class extraction after it and the
+    .npz checkpoint written by the experiment scripts — all produced by the reference's own functions."""
+    import tempfile
+    import shutil
+    import AMLsm as ref_aml                       # reference experiment script (save_network / load_network)
+    tmp = tempfile.mkdtemp()
+    out = {}
+    try:
+        rs = np.random.RandomState(99)
+        n_feat, n_pers = 40, 12
+        table = rs.lognormal(1.0, 0.8, size=(n_feat, n_pers))
+        table[7] = 3.25                            # constant feature -> NaN z-score -> dropped
+        table[19] = table[19].round(1)
+        with open(os.path.join(tmp, "toy.tsv"), "w") as f:
+            f.write("gene\t" + "\t".join("P%02d" % i for i in range(n_pers)) + "\n")
+            for i in range(n_feat):
+                f.write("G%03d\t" % i + "\t".join("%.6f" % x for x in table[i]) + "\n")
+        out["table_text"] = np.frombuffer(open(os.path.join(tmp, "toy.tsv"), "rb").read(), dtype=np.uint8)
+        cases = {"a": dict(holdout=0.25, repeats=1, clip=None, shuffle=True, seed=11, transform=False),
+                 "b": dict(holdout=0.2, repeats=3, clip=(-1.0, 1.0), shuffle=False, seed=12, transform=False),
+                 "c": dict(holdout=0.0, repeats=2, clip=None, shuffle=True, seed=13, transform=True)}
+        for name, c in cases.items():
+            np.random.seed(c["seed"])
+            tr, va = ref_utils.load_n_preprocess_data("toy.tsv", dtype="float64", holdout=c["holdout"], clip=c["clip"],
+                                                      transform_fn=np.power if c["transform"] else None, exponent=0.5,
+                                                      repeats=c["repeats"], shuffle=c["shuffle"], datadir=tmp)
+            out["prep_%s_train" % name] = tr.get_value()
+            out["prep_%s_val" % name] = va.get_value() if va is not None else np.zeros((0, 0))
+        # class extraction
+        bits = (rs.rand(40, 5) > 0.45).astype(np.float64)
+        bits[5:12] = bits[0]
+        bits[20:29] = bits[1]
+        labels, dist = ref_utils.find_unique_classes(bits)
+        out["cls_bits"], out["cls_labels"], out["cls_dist"] = bits, labels, dist
+        for n in (2, 3, 5):
+            out["cls_remap_%d" % n] = ref_utils.remap_class(labels.astype(int), dist, n)
+        # checkpoint written by the reference
+        rng = np.random.RandomState(5)
+
+        def net(n_ins, sizes, gauss=True):
+            with redirect_stdout(io.StringIO()):
+                d = ref_dbn.DBN(numpy_rng=rng, n_ins=n_ins, gauss=gauss, hidden_layers_sizes=sizes[:-1], n_outs=sizes[-1])
+            for p_ in d.params:
+                if p_.name == "b":
+                    p_.set_value(rng.randn(*p_.get_value().shape))
+            return d
+        me, ge, sm, top = net(9, [4]), net(13, [6, 3]), net(7, [5]), net(12, [6, 2], gauss=False)
+        classes = np.arange(6) % 3
+        ref_aml.save_network(classes, ge, me, sm, None, top, 0.1, "ref_ckpt.npz", tmp, 2)
+        shutil.copy(os.path.join(tmp, "ref_ckpt.npz"), os.path.join(HERE, "ref_checkpoint.npz"))
+        x = rng.randn(4, 13)
+        out["ckpt_ge_in"], out["ckpt_ge_out"] = x, ge.get_output(theano.shared(x))
+        # and read back by the reference's own loader
+        np_load = np.load                          # the reference predates allow_pickle=False (NumPy 1.16.3)
+        np.load = lambda *a, **k: np_load(*a, **dict(k, allow_pickle=True))
+        try:
+            with redirect_stdout(io.StringIO()):
+                me2, ge2, sm2, _, top2 = ref_aml.load_network("ref_ckpt.npz", tmp)
+        finally:
+            np.load = np_load
+        out["ckpt_roundtrip_ok"] = np.array([np.array_equal(a.get_value(), b.get_value())
+                                             for a, b in zip(ge.params + top.params, ge2.params + top2.params)])
+    finally:
+        shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(HERE, "io_cases.npz"), **out)
+    print("io_cases:", sorted(out))
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["io"]:          # only the 8f rows (the other files are unchanged by it)
+        io_case()
+        sys.exit(0)
     phases_case("phases_rbm", O.RBM, 13, 7, 5, seed=11)
     phases_case("phases_grbm", O.GRBM, 13, 7, 5, seed=12)
     phases_case("phases_grbm_noisy", O.GRBM, 13, 7, 5, seed=13, ef=False)
@@ -338,3 +410,4 @@ if __name__ == "__main__":
              lrs=[0.1, 0.1, 0.1], lambda_1=0.0, lambda_2=0.1, gauss=False, seed=52, shuffle_seed=778)
     minibatch_case()
     mdbn_case("mdbn_small")
+    io_case()

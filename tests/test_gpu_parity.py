@@ -537,3 +537,23 @@ def test_run_steps_equals_single_steps(kind, pcd, V, H, B):
     if pcd:
         assert np.array_equal(P1.get_value(), P2.get_value())
         assert int(r1.bit_i_idx.item()) == int(r2.bit_i_idx.item()) == (n + 1) % V
+
+
+# ---------------------------------------------------------------------------
+# 8f: a checkpoint written by the reference's save_network loads into working DBNs
+# ---------------------------------------------------------------------------
+def test_reference_checkpoint_loads_and_propagates(tmp_path):
+    m = M()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io_cases.npz"))
+    ref = os.path.join(os.path.dirname(__file__), "golden", "ref_checkpoint.npz")
+    me, ge, sm, dm, top = m.io.load_network(os.path.basename(ref), os.path.dirname(ref),
+                                            dbn_factory=lambda **kw: m.DBN(verbose=False, **kw))
+    assert dm is None and ge.number_of_nodes() == [13, 6, 3] and isinstance(top.rbm_layers[0], m.RBM)
+    assert isinstance(ge.rbm_layers[0], m.GRBM)
+    out = ge.get_output(g["ckpt_ge_in"].astype(np.float32))
+    close(out, g["ckpt_ge_out"], rtol=1e-5, scale=1.0, what="get_output of the loaded GE network")
+    # and back: what we write, the same loader reads
+    m.io.save_network(np.arange(4), ge, me, sm, None, top, 0.1, "rt.npz", str(tmp_path), 2)
+    me2, ge2, sm2, _, top2 = m.io.load_network("rt.npz", str(tmp_path), dbn_factory=lambda **kw: m.DBN(verbose=False, **kw))
+    for a, b in zip(ge.params + top.params, ge2.params + top2.params):
+        assert np.array_equal(a.get_value(), b.get_value())
