@@ -155,7 +155,9 @@ __device__ __forceinline__ void grid_wait(unsigned long long* bar, unsigned long
   __syncthreads();
 }
 
-template <int BT>
+// CHAIN = false is the single-step instantiation (the step loop folds away: same code as before chaining
+// existed, which measures ~4 % faster per step than the looped build); CHAIN = true runs p.n_steps steps.
+template <int BT, bool CHAIN>
 __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant__ CUtensorMap tmR,
                                                           const __grid_constant__ CUtensorMap tm8, const Params p) {
   constexpr int BTP = (BT + 3) / 4 * 4, BTS = BTP;
@@ -189,8 +191,6 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   int dbg_i = 0;
   const int F = p.dbg_flags;
   int step = 0;                                  // minibatch of this launch being processed
-  const int* idxp = p.idx;                       // its row numbers
-  uint32_t c2s = p.c2, c3s = p.c3;               // its Philox offset (rng.offset + step)
   auto mark = [&]() {
     if (p.dbg && cta == 0 && tid == 0 && step == 0) {
       unsigned long long t;
@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     RngSeg s;
     s.mode = p.rng_mode;
     s.seg = p.ubuf ? p.ubuf + off : nullptr;
-    s.k0 = p.k0; s.k1 = p.k1; s.c1 = ordinal; s.c2 = c2s; s.c3 = c3s;
+    // Philox offset of this step = rng.offset + step (recomputed here: nothing per-step is kept live across
+    // the streaming loops, which run at 255 registers)
+    const unsigned long long off64 = (((unsigned long long)p.c3 << 32) | p.c2) + (unsigned long long)step;
+    s.k0 = p.k0; s.k1 = p.k1; s.c1 = ordinal; s.c2 = (uint32_t)off64; s.c3 = (uint32_t)(off64 >> 32);
     return s;
   };
 
@@ -321,20 +324,45 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   //      the staging buffer: it is rebuilt from the sums afterwards anyway), then every element goes to the
   //      fixed-point accumulator with one red.global.add.u64; CTAs start at staggered offsets ----
   auto flush_sums = [&](float2 (&acc)[BTP / 2][4], unsigned long long* dst) {
-    float4* stage = reinterpret_cast<float4*>(hs);
-    const int ldh4 = ldh >> 2;
-    for (int gg = 0; gg < p.G; ++gg) {
-      if (col_ok && g == gg) {
+    if (p.G <= 2) {
+      // wide layers (one or two row groups): add in place in hs, group after group
+      float4* stage = reinterpret_cast<float4*>(hs);
+      const int ldh4 = ldh >> 2;
+      for (int gg = 0; gg < p.G; ++gg) {
+        if (col_ok && g == gg) {
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          float4 a = (b & 1) ? make_float4(acc[b >> 1][0].y, acc[b >> 1][1].y, acc[b >> 1][2].y, acc[b >> 1][3].y)
-                             : make_float4(acc[b >> 1][0].x, acc[b >> 1][1].x, acc[b >> 1][2].x, acc[b >> 1][3].x);
-          if (gg > 0) {
-            const float4 o = stage[b * ldh4 + q];
-            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          for (int b = 0; b < BT; ++b) {
+            float4 a = (b & 1) ? make_float4(acc[b >> 1][0].y, acc[b >> 1][1].y, acc[b >> 1][2].y, acc[b >> 1][3].y)
+                               : make_float4(acc[b >> 1][0].x, acc[b >> 1][1].x, acc[b >> 1][2].x, acc[b >> 1][3].x);
+            if (gg > 0) {
+              const float4 o = stage[b * ldh4 + q];
+              a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            }
+            stage[b * ldh4 + q] = a;
           }
-          stage[b * ldh4 + q] = a;
         }
+        __syncthreads();
+      }
+    } else {
+      // narrow layers have 4-32 row groups: every (group, quad) thread parks its rows in the idle tile ring,
+      // then each (b, quad) is summed over the groups in fixed order — two block barriers whatever G is
+      float4* park = reinterpret_cast<float4*>(smem);
+      if (col_ok) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          park[(g * BT + b) * p.CQ + q] =
+              (b & 1) ? make_float4(acc[b >> 1][0].y, acc[b >> 1][1].y, acc[b >> 1][2].y, acc[b >> 1][3].y)
+                      : make_float4(acc[b >> 1][0].x, acc[b >> 1][1].x, acc[b >> 1][2].x, acc[b >> 1][3].x);
+      }
+      __syncthreads();
+      for (int e = tid; e < BT * p.CQ; e += NT) {
+        const int b = e / p.CQ, qq = e - b * p.CQ;
+        float4 a = park[b * p.CQ + qq];
+        for (int gg = 1; gg < p.G; ++gg) {
+          const float4 o = park[(gg * BT + b) * p.CQ + qq];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
+        *reinterpret_cast<float4*>(hs + b * ldh + 4 * qq) = a;
       }
       __syncthreads();
     }
@@ -455,24 +483,36 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   // Steps of one launch need no extra synchronisation: a CTA only ever reads ITS rows of W, W_speed and vb;
   // what crosses CTAs (hidden bias, persistent chain, accumulators, cost partials) is written after the last
   // barrier of step s and read after the first barrier of step s+1.
-  for (step = 0; step < p.n_steps; ++step) {
-  idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
-  {
-    const unsigned long long off64 = (((unsigned long long)p.c3 << 32) | p.c2) + (unsigned long long)step;
-    c2s = (uint32_t)off64; c3s = (uint32_t)(off64 >> 32);
-  }
-  unsigned long long* const accp = (step & 1) ? p.acc_other : p.acc;
-  unsigned long long* const acc_prev = (step & 1) ? p.acc : p.acc_other;
-  unsigned long long* const A0 = accp;
-  unsigned long long* const A1 = accp + p.n_acc;
-  auto GA = [&](int s) { return accp + (size_t)(2 + s % 3) * p.n_acc; };
+  const int n_steps = CHAIN ? p.n_steps : 1;
+  for (step = 0; step < n_steps; ++step) {
+  // accumulator set of this step / of the previous one (alternating), recomputed where they are needed
+  auto acc_set = [&]() { return (step & 1) ? p.acc_other : p.acc; };
+  auto GA = [&](int s) { return acc_set() + (size_t)(2 + s % 3) * p.n_acc; };
+#define A0 (acc_set())
+#define A1 (acc_set() + p.n_acc)
 
   // ---- gather v0 slab: v0s[r][b] = data[idx[b]][row0 + r]; rows >= `rows` and b >= B are zero -----
   if (!(F & 2)) issue(0, p.nslots);     // start streaming W while the minibatch is gathered
   for (int r = tid; r < p.rows_alloc; r += NT) vbs[r] = r < rows ? __ldcg(&p.vb[row0 + r]) : 0.f;
   // the minibatch row numbers first (one dependent load for everybody), then eight gathers in flight per thread
   int* sidx = reinterpret_cast<int*>(misc) + 32;
+  const int* idxp = p.idx ? p.idx + (size_t)step * B : nullptr;      // row numbers of this step's minibatch
   if (tid < BTS) sidx[tid] = tid < B ? (idxp ? idxp[tid] : tid) : -1;
+  // small vectors that are only needed after the first barrier or in the last pass: pull them into L2 now
+  // (with the weights of several layers in rotation they have been evicted since the previous step)
+  {
+    auto pf = [](const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+    const int hb_lines = (H * 4 + 127) / 128, sv_lines = (rows * 4 + 127) / 128 + 1;
+    if (tid < hb_lines) pf(reinterpret_cast<const char*>(p.hb) + tid * 128);
+    else if (tid < hb_lines + sv_lines && rows > 0)
+      pf(reinterpret_cast<const char*>(p.Svb + row0) + min((tid - hb_lines) * 128, rows * 4 - 4));
+    else if (cta == (int)gridDim.x - 1 && tid < 2 * hb_lines + sv_lines)
+      pf(reinterpret_cast<const char*>(p.Shb) + (tid - hb_lines - sv_lines) * 128);
+    if (p.pcd) {
+      const int p_lines = (B * H * 4 + 127) / 128;
+      for (int i = cta * NT + tid; i < p_lines; i += gridDim.x * NT) pf(reinterpret_cast<const char*>(p.P) + (size_t)i * 128);
+    }
+  }
   // pseudo-likelihood monitor: the CTA that will compute it for minibatch row pl_b fetches its scalars now
   // (three dependent loads that would otherwise sit on that CTA's critical path)
   if (pl_cta && tid == NT - 1) {
@@ -542,7 +582,10 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   // every CTA is past the previous step now: the hidden bias it wrote is final, and nobody reads the
   // accumulator set of the previous step (or launch) any more -> clear it for the next one
   for (int j = tid; j < ldh; j += NT) hbs[j] = j < H ? __ldcg(&p.hb[j]) : 0.f;
-  for (int i = cta * NT + tid; i < 5 * p.n_acc; i += gridDim.x * NT) __stcg(&acc_prev[i], 0ULL);
+  {
+    unsigned long long* acc_prev = (step & 1) ? p.acc : p.acc_other;
+    for (int i = cta * NT + tid; i < 5 * p.n_acc; i += gridDim.x * NT) __stcg(&acc_prev[i], 0ULL);
+  }
   // positive-phase means as fp32 for the statistics pass: every CTA converts one slice (published by the
   // barriers that follow), so that pass does not pay a sum -> mean round trip.  Loads first, the chain
   // state is rebuilt while they are in flight.
@@ -759,33 +802,42 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
 #pragma unroll
     for (int b = 0; b < BT; ++b)
       ph[b] = col_ok ? __ldcg(reinterpret_cast<const float4*>(p.PHf + b * ldw + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-      // every thread converts the sums of its own columns, ten rows (20 L2 loads) in flight at a time; no
-      // shared-memory round, no block barrier
+    if constexpr (BT <= 10) {
+      // every thread converts the sums of its own columns: all loads in flight, no shared-memory round
       const unsigned long long* GL = GA(p.k - 1);
       const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * (col_ok ? q : 0));
+      longlong2 t[BT][2];
 #pragma unroll
-      for (int b0 = 0; b0 < BT; b0 += 10) {
-        longlong2 t[10][2];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int b = b0 + i;
-          t[i][0] = t[i][1] = make_longlong2(0, 0);
-          if (col_ok && b < B) {
-            const longlong2* sp = reinterpret_cast<const longlong2*>(GL + b * ldw + 4 * q);
-            t[i][0] = __ldcg(sp);
-            t[i][1] = __ldcg(sp + 1);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int b = b0 + i;
-          nh[b] = (col_ok && b < B)
-                      ? make_float4(sigmoid_fast_(from_fixed(t[i][0].x) + hb4.x), sigmoid_fast_(from_fixed(t[i][0].y) + hb4.y),
-                                    sigmoid_fast_(from_fixed(t[i][1].x) + hb4.z), sigmoid_fast_(from_fixed(t[i][1].y) + hb4.w))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < BT; ++b) {
+        t[b][0] = t[b][1] = make_longlong2(0, 0);
+        if (col_ok && b < B) {
+          const longlong2* sp = reinterpret_cast<const longlong2*>(GL + b * ldw + 4 * q);
+          t[b][0] = __ldcg(sp);
+          t[b][1] = __ldcg(sp + 1);
         }
       }
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        nh[b] = (col_ok && b < B)
+                    ? make_float4(sigmoid_fast_(from_fixed(t[b][0].x) + hb4.x), sigmoid_fast_(from_fixed(t[b][0].y) + hb4.y),
+                                  sigmoid_fast_(from_fixed(t[b][1].x) + hb4.z), sigmoid_fast_(from_fixed(t[b][1].y) + hb4.w))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      // (the BT = 20 instantiation has no registers for 40 loads in flight next to ph and nh)
+      sums_to_hs(GA(p.k - 1));
+      const int n = B * p.CQ;
+#pragma unroll 1
+      for (int e = tid; e < n; e += NT) {
+        const int b = e / p.CQ, j0 = 4 * (e - b * p.CQ);
+        float4* hp = reinterpret_cast<float4*>(hs + b * ldh + j0);
+        const float4 x = *hp, hb4 = *reinterpret_cast<const float4*>(hbs + j0);
+        *hp = make_float4(sigmoid_fast_(x.x + hb4.x), sigmoid_fast_(x.y + hb4.y), sigmoid_fast_(x.z + hb4.z),
+                          sigmoid_fast_(x.w + hb4.w));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        nh[b] = col_ok ? *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int ncol = min(4, H - 4 * q);
     for (int j = 0, stg = 0; j < ntiles_s; ++j, stg = (stg + 1 == depth ? 0 : stg + 1)) {
@@ -880,19 +932,17 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
         }
       }
     }
-    if (cta == 0 && tid == 0) {
-      float c;
-      if (p.pcd) {
-        c = 0.f;
-        for (int b = 0; b < B; ++b) c += __ldcg(&p.cost_part[b]);
-        c *= p.cost_scale;
-        if (step == p.n_steps - 1) *p.bit_idx = (bit0 + p.n_steps) % V;     // :445
-      } else {
-        c = 0.f;
-        for (int i = 0; i < (int)gridDim.x; ++i) c += __ldcg(&p.cost_part[i]);
-        c *= p.cost_scale;
+    if (cta == 0 && warp == 0) {
+      // cost = fixed-order sum of the per-CTA (CD) / per-row (PCD) partials: the loads of one lane are
+      // independent and in flight together, the lanes are combined by the fixed shuffle tree
+      const int n = p.pcd ? B : (int)gridDim.x;
+      float c = 0.f;
+      for (int i = lane; i < n; i += 32) c += __ldcg(&p.cost_part[i]);
+      c = warp_sum(c) * p.cost_scale;
+      if (lane == 0) {
+        if (p.pcd && step == n_steps - 1) *p.bit_idx = (bit0 + n_steps) % V;     // :445
+        if (p.cost_out) p.cost_out[step] = c;
       }
-      if (p.cost_out) p.cost_out[step] = c;
     }
   }
 
@@ -901,6 +951,8 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   }   // step
+#undef A0
+#undef A1
 
   // reset the barrier for the next launch: the last CTA out switches off the lights
   __syncthreads();
@@ -992,6 +1044,12 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.nslots = (int)((smem_max - fixed) / g.slot_bytes);
   if (g.nslots > MAX_SLOTS) g.nslots = MAX_SLOTS;
   g.ring_bytes = g.nslots * g.slot_bytes;
+  {
+    // the flush parks G x BT x CQ float4 partials in the ring
+    const size_t park = g.G > 2 ? (size_t)g.G * g.BT * g.CQ * 16 : 0;
+    if ((size_t)g.ring_bytes < park) g.ring_bytes = (int)((park + 1023) & ~(size_t)1023);
+    if (fixed + (size_t)g.ring_bytes > smem_max) return g;
+  }
   const int narr = a.weightcost != 0.f ? 3 : 2;
   if ((size_t)narr * ((8 * a.ldw * 4 + 127) & ~127) > (size_t)g.ring_bytes) return g;
   size_t off = (size_t)g.ring_bytes;
@@ -1010,10 +1068,10 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   return g;
 }
 
-template <int BT>
+template <int BT, bool CHAIN>
 static int launch(mdbn_ctx* c, const CUtensorMap* tms, const Params& p, const Geometry& g, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kfn = cd_skinny_kernel<BT>;
+  auto kfn = cd_skinny_kernel<BT, CHAIN>;
   if (!configured[c->device]) {
     MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[c->device] = true;
@@ -1097,8 +1155,8 @@ int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_
   MDBN_TRY(sk::make_map(&tms[0], a.W, a.V, a.ldw, g.R));
   MDBN_TRY(sk::make_map(&tms[1], a.W, a.V, a.ldw, 8));
   int rc = 2;
-  if (g.BT == 10) rc = sk::launch<10>(c, tms, p, g, st);
-  else if (g.BT == 20) rc = sk::launch<20>(c, tms, p, g, st);
+  if (g.BT == 10) rc = n_steps > 1 ? sk::launch<10, true>(c, tms, p, g, st) : sk::launch<10, false>(c, tms, p, g, st);
+  else if (g.BT == 20) rc = n_steps > 1 ? sk::launch<20, true>(c, tms, p, g, st) : sk::launch<20, false>(c, tms, p, g, st);
   else set_error("skinny path: no kernel for BT=%d", g.BT);
   if (rc == 0 && p.dbg) {
     unsigned long long t[16];
