@@ -11,9 +11,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmdbn_b200.so")
 
 RBM, GRBM = 0, 1
 RNG_NONE, RNG_BUFFER, RNG_PHILOX = 0, 1, 2
-PATH_AUTO, PATH_GENERIC, PATH_SKINNY, PATH_TENSOR = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_SKINNY, PATH_TENSOR, PATH_TINY = 0, 1, 2, 3, 4
 PHASE_FULL, PHASE_STATS, PHASE_APPLY = 0, 1, 2
-PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "skinny": PATH_SKINNY, "tensor": PATH_TENSOR}
+PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "skinny": PATH_SKINNY, "tensor": PATH_TENSOR, "tiny": PATH_TINY}
 
 
 class MdbnError(RuntimeError):

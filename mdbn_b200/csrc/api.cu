@@ -160,7 +160,8 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int path = a->path;
   if (path == MDBN_PATH_AUTO) {
-    if (a->phase == MDBN_PHASE_FULL && (skinny_tc_supported(c, *a) || skinny_supported(c, *a))) path = MDBN_PATH_SKINNY;
+    if (a->phase == MDBN_PHASE_FULL && tiny_supported(c, *a)) path = MDBN_PATH_TINY;
+    else if (a->phase == MDBN_PHASE_FULL && (skinny_tc_supported(c, *a) || skinny_supported(c, *a))) path = MDBN_PATH_SKINNY;
     else if (a->tf32 && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;
     else path = MDBN_PATH_GENERIC;
   }
@@ -172,6 +173,10 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
       MDBN_CHECK(skinny_supported(c, *a), "cd_step: skinny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B,
                  a->V, a->H, a->ldw, a->phase);
       return skinny_cd_step(c, *a, st);
+    case MDBN_PATH_TINY:
+      MDBN_CHECK(tiny_supported(c, *a), "cd_step: tiny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B, a->V, a->H,
+                 a->ldw, a->phase);
+      return tiny_cd_steps(c, *a, 1, st);
     case MDBN_PATH_TENSOR:
       MDBN_CHECK(tensor_supported(c, *a), "cd_step: tensor path does not take B=%d V=%d H=%d ldw=%d", a->B, a->V, a->H,
                  a->ldw);
@@ -190,8 +195,10 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
   MDBN_CHECK(a->rng.mode == MDBN_RNG_PHILOX, "cd_steps: the PHILOX generator is required (one offset per step)");
   MDBN_CHECK(a->indices, "cd_steps: indices [n_steps][B] is required");
   // one launch when the persistent kernel takes the shape (validation happens in the first single step otherwise)
+  const bool want_tiny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_TINY;
   const bool want_skinny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_SKINNY;
-  if (want_skinny && c && a->W && !skinny_tc_supported(c, *a) && skinny_supported(c, *a)) {
+  const bool use_tiny = want_tiny && c && a->W && tiny_supported(c, *a);
+  if (use_tiny || (want_skinny && c && a->W && !skinny_tc_supported(c, *a) && skinny_supported(c, *a))) {
     MDBN_TRY(check_common(c, a->W, a->ldw, a->B, a->V, a->H));
     MDBN_CHECK(a->kind == MDBN_RBM || a->kind == MDBN_GRBM, "cd_steps: bad kind %d", a->kind);
     MDBN_CHECK(a->hbias && a->vbias && a->W_speed && a->hbias_speed && a->vbias_speed, "cd_steps: NULL parameter/state");
@@ -201,6 +208,7 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
     MDBN_CHECK(a->data && a->ld_data >= a->V, "cd_steps: bad data/ld_data");
     MDBN_CHECK(!a->persistent || a->bit_i_idx, "cd_steps: PCD needs bit_i_idx");
     MDBN_CUDA(cudaSetDevice(c->device));
+    if (use_tiny) return tiny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
     return skinny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
   }
   for (int s = 0; s < n_steps; ++s) {

@@ -1,0 +1,565 @@
+// Small layers (the upper layers of every DBN of the reference: 559->40, 400->40, 200->20, 100->24 ...):
+// CD-k / PCD-k steps on ONE THREAD-BLOCK CLUSTER with the weights resident in shared memory.
+//
+// On such layers a step is pure latency: the persistent grid kernel (skinny.cu) spends ~9 us per Gibbs
+// iteration in L2 round trips (reduction atomics, grid barrier, read-back) for a few hundred thousand FMAs.
+// Here the 8 CTAs of one cluster each own V/8 rows of W and of its momentum and keep them in shared memory
+// for the whole launch (an epoch of chained steps touches global memory only for the minibatch rows);
+// the hidden pre-activations are all-reduced through DISTRIBUTED SHARED MEMORY (every CTA reads the eight
+// partials with ld.shared::cluster and adds them in rank order: deterministic) behind one
+// barrier.cluster per propagation; bias, sigmoid and the Bernoulli draw are then computed by every CTA
+// for the whole [B, H] (the draws are indexed by element, so all CTAs agree).  Same arithmetic contract
+// as the other paths: fp32, src/rbm.py semantics, Philox or caller-supplied uniforms.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "ctx.h"
+
+namespace mdbn {
+namespace tn {
+
+constexpr int NT = 512;
+constexpr int CL = 8;            // CTAs per cluster (portable maximum)
+
+struct Params {
+  float *W, *S;
+  const float* Wsnap;
+  int ldw;
+  float *hb, *vb, *Shb, *Svb;
+  const float* data;
+  long long ld_data;
+  const int* idx;
+  float* P;
+  int* bit_idx;
+  float* cost_out;
+  int kind, B, V, H, k, pcd, n_steps;
+  float inv_bnom, inv_b, wc, c1, decay, mom, lr, cost_scale;
+  int rng_mode;
+  const float* ubuf;
+  uint32_t k0, k1, c2, c3;
+  long long u_step_stride, u_off_v, u_off_h;
+  int rows_per_cta, rows_alloc, BTS, CQ, G;
+  unsigned long long* dbg;   // optional phase timeline (MDBN_TINY_TIMING=1), rank 0, first step
+  // shared-memory byte offsets
+  int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb,
+      off_shb, off_misc;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// float4 from the same shared-memory offset of CTA `rank` of this cluster
+__device__ __forceinline__ float4 ld_remote4(const void* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_remote1(const void* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast_(float x) { return rcp_approx(1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* Ws = reinterpret_cast<float*>(smem + p.off_W);       // [rows_alloc][ldw]  resident weights of the owned rows
+  float* Ss = reinterpret_cast<float*>(smem + p.off_S);       // [rows_alloc][ldw]  resident momentum
+  float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows_alloc][BTS]  data
+  float* nvs = reinterpret_cast<float*>(smem + p.off_nv);     // [rows_alloc][BTS]  round(v0) (PCD pass 0), then nv mean
+  float* vin = reinterpret_cast<float*>(smem + p.off_vin);    // [rows_alloc][BTS]  visible input of the next propup
+  float* hs = reinterpret_cast<float*>(smem + p.off_hs);      // [BTS][ldw]  chain state
+  float* pc = reinterpret_cast<float*>(smem + p.off_pc);      // [BTS][ldw]  persistent chain (PCD)
+  float* phs = reinterpret_cast<float*>(smem + p.off_ph);     // [BTS][ldw]  positive-phase means
+  float* nhs = reinterpret_cast<float*>(smem + p.off_nh);     // [BTS][ldw]  last negative means / PL pre-activations
+  float* part = reinterpret_cast<float*>(smem + p.off_part);  // [2 parity][2 sets][BTS][ldw] partial hidden sums
+  float* vbs = reinterpret_cast<float*>(smem + p.off_vb);     // [rows_alloc]
+  float* svbs = reinterpret_cast<float*>(smem + p.off_svb);   // [rows_alloc]
+  float* hbs = reinterpret_cast<float*>(smem + p.off_hb);     // [ldw]
+  float* shbs = reinterpret_cast<float*>(smem + p.off_shb);   // [ldw]
+  float* park = reinterpret_cast<float*>(smem + p.off_park);  // [G][BTS][ldw] row-group partials of a propup
+  float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, [40] cost partial, [48..] sidx
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_rank();
+  const int ldw = p.ldw, B = p.B, V = p.V, H = p.H, BTS = p.BTS, CQ = p.CQ;
+  const int row0 = (int)rank * p.rows_per_cta;
+  const int rows = max(0, min(p.rows_per_cta, V - row0));
+  const int nhid = BTS * ldw;                       // floats of one [BTS][ldw] panel
+  int parity = 0;
+  int dbg_i = 0;
+  auto mark = [&]() {
+    if (p.dbg && rank == 0 && tid == 0 && dbg_i < 16) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[dbg_i++] = t;
+    }
+  };
+  mark();
+
+  // ---- load the resident state ----
+  for (int e = tid; e < p.rows_alloc * CQ; e += NT) {
+    const int r = e / CQ, q = e - r * CQ;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s = w;
+    if (r < rows) {
+      w = *reinterpret_cast<const float4*>(p.W + (size_t)(row0 + r) * ldw + 4 * q);
+      s = *reinterpret_cast<const float4*>(p.S + (size_t)(row0 + r) * ldw + 4 * q);
+    }
+    *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q) = w;
+    *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q) = s;
+  }
+  for (int r = tid; r < p.rows_alloc; r += NT) {
+    vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
+    svbs[r] = r < rows ? p.Svb[row0 + r] : 0.f;
+  }
+  for (int j = tid; j < ldw; j += NT) {
+    hbs[j] = j < H ? p.hb[j] : 0.f;
+    shbs[j] = j < H ? p.Shb[j] : 0.f;
+  }
+  for (int e = tid; e < nhid; e += NT) {
+    const int b = e / ldw, j = e - b * ldw;
+    hs[e] = phs[e] = nhs[e] = 0.f;
+    pc[e] = (p.pcd && b < B && j < H) ? p.P[(size_t)b * H + j] : 0.f;
+  }
+  const int bit0 = p.pcd ? *p.bit_idx : 0;
+  __syncthreads();
+  mark();   // state loaded
+
+  auto seg = [&](long long off, uint32_t ordinal, int step) {
+    RngSeg s;
+    const unsigned long long off64 = (((unsigned long long)p.c3 << 32) | p.c2) + (unsigned long long)step;
+    s.mode = p.rng_mode;
+    s.seg = p.ubuf ? p.ubuf + off : nullptr;
+    s.k0 = p.k0; s.k1 = p.k1; s.c1 = ordinal; s.c2 = (uint32_t)off64; s.c3 = (uint32_t)(off64 >> 32);
+    return s;
+  };
+
+  // ---- partial propup of the owned rows: out[b][j] = sum_r src[r][b] * W[r][j].  Item = (column quad, 4 rows
+  //      of the minibatch, row group g): the G row groups keep all threads busy on narrow layers; their
+  //      partials are added in group order ----
+  auto up_partial = [&](const float* __restrict__ src, float* __restrict__ out) {
+    const int nb4 = BTS >> 2, nq = CQ * nb4, G = p.G;
+    for (int it = tid; it < nq * G; it += NT) {
+      const int g = it / nq, rem = it - g * nq, q = rem % CQ, b4 = rem / CQ;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 2
+      for (int r = g; r < rows; r += G) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + r * ldw + 4 * q);
+        const float4 v = *reinterpret_cast<const float4*>(src + r * BTS + 4 * b4);
+        a0.x = fmaf(v.x, w.x, a0.x); a0.y = fmaf(v.x, w.y, a0.y); a0.z = fmaf(v.x, w.z, a0.z); a0.w = fmaf(v.x, w.w, a0.w);
+        a1.x = fmaf(v.y, w.x, a1.x); a1.y = fmaf(v.y, w.y, a1.y); a1.z = fmaf(v.y, w.z, a1.z); a1.w = fmaf(v.y, w.w, a1.w);
+        a2.x = fmaf(v.z, w.x, a2.x); a2.y = fmaf(v.z, w.y, a2.y); a2.z = fmaf(v.z, w.z, a2.z); a2.w = fmaf(v.z, w.w, a2.w);
+        a3.x = fmaf(v.w, w.x, a3.x); a3.y = fmaf(v.w, w.y, a3.y); a3.z = fmaf(v.w, w.z, a3.z); a3.w = fmaf(v.w, w.w, a3.w);
+      }
+      float* o = (G > 1 ? park + (size_t)g * nhid : out) + (4 * b4) * ldw + 4 * q;
+      *reinterpret_cast<float4*>(o) = a0;
+      *reinterpret_cast<float4*>(o + ldw) = a1;
+      *reinterpret_cast<float4*>(o + 2 * ldw) = a2;
+      *reinterpret_cast<float4*>(o + 3 * ldw) = a3;
+    }
+    if (G > 1) {
+      __syncthreads();
+      for (int e = tid; e < BTS * CQ; e += NT) {
+        float4 a = *reinterpret_cast<const float4*>(park + 4 * e);
+        for (int g = 1; g < G; ++g) {
+          const float4 o = *reinterpret_cast<const float4*>(park + (size_t)g * nhid + 4 * e);
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
+        *reinterpret_cast<float4*>(out + 4 * e) = a;
+      }
+      __syncthreads();
+    }
+  };
+  // ---- cluster-wide sum of a partial panel (rank order) + hidden bias; fn(b, j0, pre[4]) per quad ----
+  auto all_reduce = [&](const float* my_panel, auto&& fn) {
+    for (int it = tid; it < B * CQ; it += NT) {
+      const int b = it / CQ, q = it - b * CQ;
+      const float* lp = my_panel + b * ldw + 4 * q;
+      float4 s = ld_remote4(lp, 0);
+#pragma unroll
+      for (uint32_t c = 1; c < CL; ++c) {
+        const float4 o = ld_remote4(lp, c);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * q);
+      const float pre[4] = {s.x + hb4.x, s.y + hb4.y, s.z + hb4.z, s.w + hb4.w};
+      fn(b, 4 * q, pre);
+    }
+  };
+  auto sample4 = [&](const RngSeg& rs, int b, int j0, const float (&mean)[4], float (&out)[4]) {
+    float u[4];
+    if (rs.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
+      const long long e0 = (long long)b * H + j0;
+      const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs.c1, rs.c2, rs.c3, rs.k0, rs.k1);
+      u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) u[t] = j0 + t < H ? rng_uniform(rs, (long long)b * H + j0 + t) : 2.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) out[t] = (j0 + t < H && u[t] < mean[t]) ? 1.f : 0.f;
+  };
+
+  int* sidx = reinterpret_cast<int*>(misc) + 48;
+
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int* idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
+    // ---- gather the minibatch rows of the owned visible units ----
+    if (tid < BTS) sidx[tid] = tid < B ? (idxp ? idxp[tid] : tid) : -1;
+    __syncthreads();
+    for (int e = tid; e < p.rows_alloc * BTS; e += NT) {
+      const int b = e / p.rows_alloc, r = e - b * p.rows_alloc;
+      float x = 0.f;
+      if (r < rows && sidx[b] >= 0) x = __ldg(&p.data[(long long)sidx[b] * p.ld_data + row0 + r]);
+      v0s[r * BTS + b] = x;
+      nvs[r * BTS + b] = p.pcd ? roundf(x) : 0.f;
+    }
+    __syncthreads();
+    mark();   // gathered
+
+    // =============================== positive phase ===============================
+    {
+      float* my = part + (size_t)parity * 2 * nhid;
+      up_partial(v0s, my);
+      if (p.pcd) up_partial(nvs, my + nhid);
+      mark();
+      cluster_sync();
+      mark();
+      const RngSeg rs0 = seg(0, 0, step);
+      all_reduce(my, [&](int b, int j0, const float (&pre)[4]) {
+        const float mean[4] = {sigmoid_fast_(pre[0]), sigmoid_fast_(pre[1]), sigmoid_fast_(pre[2]), sigmoid_fast_(pre[3])};
+        *reinterpret_cast<float4*>(phs + b * ldw + j0) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+        float smp[4];
+        if (p.pcd) {                                             // chain starts from the persistent state (src/rbm.py:308-311)
+          const float4 c4 = *reinterpret_cast<const float4*>(pc + b * ldw + j0);
+          smp[0] = c4.x; smp[1] = c4.y; smp[2] = c4.z; smp[3] = c4.w;
+        } else {
+          sample4(rs0, b, j0, mean, smp);
+        }
+        *reinterpret_cast<float4*>(hs + b * ldw + j0) = make_float4(smp[0], smp[1], smp[2], smp[3]);
+      });
+      if (p.pcd && rank == 0)                                    // pre-activations of round(v0) for the monitor
+        all_reduce(my + nhid, [&](int b, int j0, const float (&pre)[4]) {
+          *reinterpret_cast<float4*>(nhs + b * ldw + j0) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+        });
+      parity ^= 1;
+      __syncthreads();
+      mark();   // positive phase done
+    }
+    // pseudo-likelihood monitor (src/rbm.py:421-447) on CTA 0: pre-update W[bit,:] and vb[bit] come from their owner
+    if (p.pcd && rank == 0) {
+      const int bit = (bit0 + step) % V;
+      const uint32_t owner = (uint32_t)(bit / p.rows_per_cta);
+      const int lr_ = bit - (int)owner * p.rows_per_cta;
+      const float vbv = ld_remote1(vbs + lr_, owner);
+      for (int b = warp; b < B; b += NT / 32) {
+        const float x = roundf(__ldg(&p.data[(long long)sidx[b] * p.ld_data + bit]));
+        const float d = 1.f - 2.f * x;
+        float h0 = 0.f, h1 = 0.f;
+        for (int j = lane; j < H; j += 32) {
+          const float pre = nhs[b * ldw + j];
+          h0 += softplusf_(pre);
+          h1 += softplusf_(pre + d * ld_remote1(Ws + lr_ * ldw + j, owner));
+        }
+        h0 = warp_sum(h0);
+        h1 = warp_sum(h1);
+        if (lane == 0) {
+          float vterm;
+          if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
+          else vterm = d * vbv;
+          misc[16 + b] = -(float)V * softplusf_((h1 - h0) + vterm);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float c = 0.f;
+        for (int b = 0; b < B; ++b) c += misc[16 + b];
+        if (p.cost_out) p.cost_out[step] = c * p.cost_scale;
+      }
+    }
+
+    // =============================== k Gibbs steps ===============================
+    float cost_acc = 0.f;
+    for (int s = 0; s < p.k; ++s) {
+      const bool last = (s == p.k - 1);
+      const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
+      const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s, step);
+      const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
+      // propdown of the owned rows (complete dot products: every CTA holds the whole chain state) + epilogue
+      const int nb4 = BTS >> 2;
+      for (int it = tid; it < rows * nb4; it += NT) {
+        const int r = it % rows, b4 = it / rows;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* wr = Ws + r * ldw;
+        const float* h0p = hs + (4 * b4) * ldw;
+#pragma unroll 2
+        for (int q = 0; q < CQ; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + 4 * q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4 h4 = *reinterpret_cast<const float4*>(h0p + t * ldw + 4 * q);
+            acc[t] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, acc[t]))));
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int b = 4 * b4 + t;
+          float v_in = 0.f, mean = 0.f;
+          if (b < B) {
+            const float pre = acc[t] + vbs[r];
+            if (p.kind == MDBN_GRBM) {
+              mean = pre;
+              v_in = pre;                                        // mean-field visible (src/rbm.py:669)
+            } else {
+              mean = sigmoidf_(pre);
+              v_in = rng_uniform(rs_v, (long long)b * V + row0 + r) < mean ? 1.f : 0.f;
+            }
+            if (last && !p.pcd) {
+              const float t0 = v0s[r * BTS + b];
+              if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t0; cost_acc += d * d; }      // :697
+              else cost_acc += t0 * softplusf_(-pre) + (1.f - t0) * softplusf_(pre);                    // :479-480
+            }
+          }
+          vin[r * BTS + b] = v_in;
+          if (last) nvs[r * BTS + b] = mean;
+        }
+      }
+      __syncthreads();
+      if (s == 0) mark();   // propdown + epilogue
+      float* my = part + (size_t)parity * 2 * nhid;
+      up_partial(vin, my);
+      if (s == 0) mark();
+      if (last && !p.pcd) {
+        const float c = block_sum(cost_acc, misc);
+        if (tid == 0) misc[40] = c;
+      }
+      cluster_sync();
+      if (s == 0) mark();
+      all_reduce(my, [&](int b, int j0, const float (&pre)[4]) {
+        const float mean[4] = {sigmoid_fast_(pre[0]), sigmoid_fast_(pre[1]), sigmoid_fast_(pre[2]), sigmoid_fast_(pre[3])};
+        float smp[4];
+        sample4(rs_h, b, j0, mean, smp);
+        const float4 s4 = make_float4(smp[0], smp[1], smp[2], smp[3]);
+        *reinterpret_cast<float4*>(hs + b * ldw + j0) = s4;
+        if (last) {
+          *reinterpret_cast<float4*>(nhs + b * ldw + j0) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+          if (p.pcd) *reinterpret_cast<float4*>(pc + b * ldw + j0) = s4;     // new persistent chain (src/rbm.py:372)
+        }
+      });
+      parity ^= 1;
+      __syncthreads();
+      if (s == 0) mark();   // Gibbs step 0 done
+    }
+    mark();   // all Gibbs steps done
+    if (!p.pcd && rank == 0 && warp == 0) {                      // reconstruction cost: rank-ordered sum of the partials
+      float c = lane < CL ? ld_remote1(misc + 40, (uint32_t)lane) : 0.f;
+      c = warp_sum(c);
+      if (lane == 0 && p.cost_out) p.cost_out[step] = c * p.cost_scale;
+    }
+
+    // =============================== statistics + update (owned rows, in shared memory) ===============================
+    for (int it = tid; it < rows * CQ; it += NT) {
+      const int r = it / CQ, q = it - r * CQ;
+      float gs[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int b = 0; b < B; ++b) {
+        const float a = v0s[r * BTS + b], n = nvs[r * BTS + b];
+        const float4 ph4 = *reinterpret_cast<const float4*>(phs + b * ldw + 4 * q);
+        const float4 nh4 = *reinterpret_cast<const float4*>(nhs + b * ldw + 4 * q);
+        gs[0] = fmaf(a, ph4.x, gs[0]); gs[0] = fmaf(-n, nh4.x, gs[0]);
+        gs[1] = fmaf(a, ph4.y, gs[1]); gs[1] = fmaf(-n, nh4.y, gs[1]);
+        gs[2] = fmaf(a, ph4.z, gs[2]); gs[2] = fmaf(-n, nh4.z, gs[2]);
+        gs[3] = fmaf(a, ph4.w, gs[3]); gs[3] = fmaf(-n, nh4.w, gs[3]);
+      }
+      float4 w4 = *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q), s4 = *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q);
+      float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.wc != 0.f) n4 = __ldg(reinterpret_cast<const float4*>(p.Wsnap + (size_t)(row0 + r) * ldw + 4 * q));
+      float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, nv4[4] = {n4.x, n4.y, n4.z, n4.w};
+      float wo[4], so[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float gw = gs[c] * p.inv_bnom - p.wc * nv4[c];                  // src/rbm.py:411-415
+        float mult = p.decay;
+        if (p.c1 != 0.f) {
+          const float t = fabsf(wv[c]) + 0.001f;                        // :347-350, one reciprocal
+          const float invD = t * rcp_approx(t + p.c1);
+          gw *= invD;
+          mult *= invD;                                                 // :353-356
+        }
+        so[c] = gw + (sv[c] - gw) * p.mom;                              // :361
+        wo[c] = 4 * q + c < H ? wv[c] * mult + sv[c] * p.lr : wv[c];    // :364 (OLD speed); padding columns stay zero
+        if (4 * q + c >= H) so[c] = sv[c];
+      }
+      *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+      *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
+    }
+    for (int r = tid; r < rows; r += NT) {                       // visible bias  src/rbm.py:417
+      float gsum = 0.f;
+      for (int b = 0; b < B; ++b) gsum += v0s[r * BTS + b] - nvs[r * BTS + b];
+      const float gb = gsum * p.inv_b, sv = svbs[r];
+      svbs[r] = gb + (sv - gb) * p.mom;
+      vbs[r] = vbs[r] + sv * p.lr;
+    }
+    __syncthreads();                                             // (phs / nhs are still read above)
+    for (int j = tid; j < H; j += NT) {                          // hidden bias  :416 — every CTA, identical result
+      float gsum = 0.f;
+      for (int b = 0; b < B; ++b) gsum += phs[b * ldw + j] - nhs[b * ldw + j];
+      const float gb = gsum * p.inv_b, sv = shbs[j];
+      shbs[j] = gb + (sv - gb) * p.mom;
+      hbs[j] = hbs[j] + sv * p.lr;
+    }
+    __syncthreads();
+    mark();   // update done
+  }   // step
+
+  // ---- write the resident state back ----
+  for (int e = tid; e < rows * CQ; e += NT) {
+    const int r = e / CQ, q = e - r * CQ;
+    *reinterpret_cast<float4*>(p.W + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ws + r * ldw + 4 * q);
+    *reinterpret_cast<float4*>(p.S + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ss + r * ldw + 4 * q);
+  }
+  for (int r = tid; r < rows; r += NT) {
+    p.vb[row0 + r] = vbs[r];
+    p.Svb[row0 + r] = svbs[r];
+  }
+  if (rank == 0) {
+    for (int j = tid; j < H; j += NT) {
+      p.hb[j] = hbs[j];
+      p.Shb[j] = shbs[j];
+    }
+    if (p.pcd) {
+      for (int e = tid; e < B * H; e += NT) {
+        const int b = e / H, j = e - b * H;
+        p.P[e] = pc[b * ldw + j];
+      }
+      if (tid == 0) *p.bit_idx = (bit0 + p.n_steps) % V;          // :445, one advance per step
+    }
+  }
+  cluster_sync();      // nobody leaves while a neighbour may still read its shared memory
+}
+
+struct Geometry {
+  int BTS, CQ, rows_per_cta, rows_alloc, G;
+  int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
+      off_misc;
+  size_t smem;
+  bool ok;
+};
+
+static Geometry plan(const mdbn_cd_args& a) {
+  Geometry g{};
+  g.ok = false;
+  if (a.B < 1 || a.B > 20 || a.ldw % 4 != 0 || a.ldw > 256 || a.V < 1) return g;
+  if (((uintptr_t)a.W | (uintptr_t)a.W_speed | (uintptr_t)a.W_snap) & 15) return g;
+  g.BTS = (a.B + 3) / 4 * 4;
+  g.CQ = a.ldw / 4;
+  g.rows_per_cta = (a.V + CL - 1) / CL;
+  g.rows_alloc = (g.rows_per_cta + 3) & ~3;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return (int)o; };
+  const size_t slab = (size_t)g.rows_alloc * a.ldw * 4, vis = (size_t)g.rows_alloc * g.BTS * 4,
+               hid = (size_t)g.BTS * a.ldw * 4;
+  g.G = NT / (g.CQ * (g.BTS / 4));
+  g.G = g.G < 1 ? 1 : (g.G > 8 ? 8 : g.G);
+  while (g.G > 1 && (size_t)g.G * hid > 48 * 1024) --g.G;
+  g.off_park = take(g.G > 1 ? (size_t)g.G * hid : 0);
+  g.off_W = take(slab); g.off_S = take(slab);
+  g.off_v0 = take(vis); g.off_nv = take(vis); g.off_vin = take(vis);
+  g.off_hs = take(hid); g.off_pc = take(hid); g.off_ph = take(hid); g.off_nh = take(hid);
+  g.off_part = take(4 * hid);
+  g.off_vb = take((size_t)g.rows_alloc * 4); g.off_svb = take((size_t)g.rows_alloc * 4);
+  g.off_hb = take((size_t)a.ldw * 4); g.off_shb = take((size_t)a.ldw * 4);
+  g.off_misc = take(512);
+  g.smem = off;
+  g.ok = g.smem <= 200 * 1024;
+  return g;
+}
+
+}  // namespace tn
+
+bool tiny_supported(const mdbn_ctx*, const mdbn_cd_args& a) {
+  if (a.phase != MDBN_PHASE_FULL) return false;
+  return tn::plan(a).ok;
+}
+
+// n_steps consecutive steps in one launch (a.indices [n_steps][B], a.cost_out [n_steps]; PHILOX when n_steps > 1)
+int tiny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t st) {
+  tn::Geometry g = tn::plan(a);
+  MDBN_CHECK(g.ok, "tiny path: unsupported shape");
+  MDBN_CHECK(n_steps >= 1, "tiny path: n_steps must be >= 1");
+  MDBN_CHECK(n_steps == 1 || a.rng.mode == MDBN_RNG_PHILOX, "tiny path: chained steps need the PHILOX generator");
+  tn::Params p{};
+  p.W = a.W; p.S = a.W_speed; p.Wsnap = a.weightcost != 0.f ? a.W_snap : nullptr; p.ldw = a.ldw;
+  p.hb = a.hbias; p.vb = a.vbias; p.Shb = a.hbias_speed; p.Svb = a.vbias_speed;
+  p.data = a.data; p.ld_data = a.ld_data; p.idx = a.indices;
+  p.P = a.persistent; p.bit_idx = a.bit_i_idx; p.cost_out = a.cost_out;
+  p.kind = a.kind; p.B = a.B; p.V = a.V; p.H = a.H; p.k = a.k; p.pcd = a.persistent != nullptr; p.n_steps = n_steps;
+  p.inv_bnom = 1.0f / (float)a.B_nom;
+  p.inv_b = 1.0f / (float)a.B;
+  p.wc = a.weightcost;
+  p.c1 = (2.0f * a.lr) * a.lambda_1;
+  p.decay = 1.0f - (2.0f * a.lr) * a.lambda_2;
+  p.mom = a.momentum; p.lr = a.lr;
+  p.cost_scale = (!p.pcd && a.kind == MDBN_GRBM) ? 1.0f / ((float)a.B * (float)a.V) : 1.0f / (float)a.B;
+  p.rng_mode = a.rng.mode;
+  p.ubuf = a.rng.mode == MDBN_RNG_BUFFER ? a.rng.buffer : nullptr;
+  p.k0 = (uint32_t)a.rng.seed; p.k1 = (uint32_t)(a.rng.seed >> 32);
+  p.c2 = (uint32_t)a.rng.offset; p.c3 = (uint32_t)(a.rng.offset >> 32);
+  ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
+  p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
+  p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.BTS = g.BTS; p.CQ = g.CQ; p.G = g.G;
+  p.off_park = g.off_park;
+  p.off_W = g.off_W; p.off_S = g.off_S; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vin = g.off_vin;
+  p.off_hs = g.off_hs; p.off_pc = g.off_pc; p.off_ph = g.off_ph; p.off_nh = g.off_nh; p.off_part = g.off_part;
+  p.off_vb = g.off_vb; p.off_svb = g.off_svb; p.off_hb = g.off_hb; p.off_shb = g.off_shb; p.off_misc = g.off_misc;
+
+  static bool configured[64] = {};
+  if (!configured[c->device]) {
+    MDBN_CUDA(cudaFuncSetAttribute(tn::cd_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[c->device] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tn::CL);
+  cfg.blockDim = dim3(tn::NT);
+  cfg.dynamicSmemBytes = g.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = tn::CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static const bool want_timing = getenv("MDBN_TINY_TIMING") != nullptr;
+  p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 32 : nullptr;
+  MDBN_CUDA(cudaLaunchKernelEx(&cfg, tn::cd_tiny_kernel, p));
+  c->launches++;
+  if (p.dbg) {
+    unsigned long long t[16];
+    MDBN_CUDA(cudaStreamSynchronize(st));
+    MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[tiny timeline us] V=%d H=%d B=%d k=%d G=%d:", a.V, a.H, a.B, a.k, g.G);
+    for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+  return 0;
+}
+
+}  // namespace mdbn

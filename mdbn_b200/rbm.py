@@ -252,7 +252,7 @@ class TrainFn:
         a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), phase
         if phase != _lib.PHASE_FULL:
             a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
-            if a.path == _lib.PATH_SKINNY or phase == _lib.PHASE_APPLY:
+            if a.path in (_lib.PATH_SKINNY, _lib.PATH_TINY) or phase == _lib.PHASE_APPLY:
                 a.path = _lib.PATH_AUTO      # the update from reduced statistics is one elementwise kernel
         stream = _stream() if stream is None else stream
         if n_steps > 1:

@@ -1,6 +1,6 @@
 import os, sys
 sys.path.insert(0, "/root/repo")
-os.environ["MDBN_SKINNY_TIMING"] = "1"
+os.environ["MDBN_SKINNY_TIMING"] = "1"; os.environ["MDBN_TINY_TIMING"] = "1"
 import numpy as np, torch
 import mdbn_b200 as M
 for (cls, V, H, B, k) in ((M.RBM, 100, 24, 20, 1), (M.RBM, 400, 40, 20, 1), (M.GRBM, 559, 40, 20, 10), (M.GRBM, 1686, 200, 20, 1)):

@@ -119,7 +119,7 @@ def run_cd_golden(g, path):
     return r, P, np.array(costs)
 
 
-@pytest.mark.parametrize("path", ["generic", "skinny", "auto"])
+@pytest.mark.parametrize("path", ["generic", "skinny", "tiny", "auto"])
 @pytest.mark.parametrize("name", CD_CASES)
 def test_cd_sequences_vs_golden(name, path):
     g = load(name)
