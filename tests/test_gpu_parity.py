@@ -557,3 +557,18 @@ def test_reference_checkpoint_loads_and_propagates(tmp_path):
     me2, ge2, sm2, _, top2 = m.io.load_network("rt.npz", str(tmp_path), dbn_factory=lambda **kw: m.DBN(verbose=False, **kw))
     for a, b in zip(ge.params + top.params, ge2.params + top2.params):
         assert np.array_equal(a.get_value(), b.get_value())
+
+
+# ---------------------------------------------------------------------------
+# the opt-in tcgen05 edition of the skinny kernel (MDBN_SKINNY_TC=1, csrc/skinny_tc.cu) stays parity-green
+# ---------------------------------------------------------------------------
+def test_skinny_tc_opt_in_subprocess():
+    import subprocess
+    import sys
+    if os.environ.get("MDBN_SKINNY_TC"):
+        pytest.skip("already inside the opt-in run")
+    env = dict(os.environ, MDBN_SKINNY_TC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
+                        "-k", "config_shapes and auto"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
