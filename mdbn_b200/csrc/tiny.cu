@@ -38,7 +38,7 @@ struct Params {
   const float* ubuf;
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
-  int rows_per_cta, rows_alloc, BTS, CQ, G;
+  int rows_per_cta, rows_alloc, BTS, CQ, G, lds;
   unsigned long long* dbg;   // optional phase timeline (MDBN_TINY_TIMING=1), rank 0, first step
   // shared-memory byte offsets
   int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb,
@@ -81,8 +81,8 @@ __device__ __forceinline__ float sigmoid_fast_(float x) { return rcp_approx(1.0f
 
 __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  float* Ws = reinterpret_cast<float*>(smem + p.off_W);       // [rows_alloc][ldw]  resident weights of the owned rows
-  float* Ss = reinterpret_cast<float*>(smem + p.off_S);       // [rows_alloc][ldw]  resident momentum
+  float* Ws = reinterpret_cast<float*>(smem + p.off_W);       // [rows_alloc][lds]  resident weights of the owned rows (lds/4 odd: conflict-free row walks)
+  float* Ss = reinterpret_cast<float*>(smem + p.off_S);       // [rows_alloc][lds]  resident momentum
   float* v0s = reinterpret_cast<float*>(smem + p.off_v0);     // [rows_alloc][BTS]  data
   float* nvs = reinterpret_cast<float*>(smem + p.off_nv);     // [rows_alloc][BTS]  round(v0) (PCD pass 0), then nv mean
   float* vin = reinterpret_cast<float*>(smem + p.off_vin);    // [rows_alloc][BTS]  visible input of the next propup
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_rank();
-  const int ldw = p.ldw, B = p.B, V = p.V, H = p.H, BTS = p.BTS, CQ = p.CQ;
+  const int ldw = p.ldw, lds = p.lds, B = p.B, V = p.V, H = p.H, BTS = p.BTS, CQ = p.CQ;
   const int row0 = (int)rank * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, V - row0));
   const int nhid = BTS * ldw;                       // floats of one [BTS][ldw] panel
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       w = *reinterpret_cast<const float4*>(p.W + (size_t)(row0 + r) * ldw + 4 * q);
       s = *reinterpret_cast<const float4*>(p.S + (size_t)(row0 + r) * ldw + 4 * q);
     }
-    *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q) = w;
-    *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q) = s;
+    *reinterpret_cast<float4*>(Ws + r * lds + 4 * q) = w;
+    *reinterpret_cast<float4*>(Ss + r * lds + 4 * q) = s;
   }
   for (int r = tid; r < p.rows_alloc; r += NT) {
     vbs[r] = r < rows ? p.vb[row0 + r] : 0.f;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll 2
       for (int r = g; r < rows; r += G) {
-        const float4 w = *reinterpret_cast<const float4*>(Ws + r * ldw + 4 * q);
+        const float4 w = *reinterpret_cast<const float4*>(Ws + r * lds + 4 * q);
         const float4 v = *reinterpret_cast<const float4*>(src + r * BTS + 4 * b4);
         a0.x = fmaf(v.x, w.x, a0.x); a0.y = fmaf(v.x, w.y, a0.y); a0.z = fmaf(v.x, w.z, a0.z); a0.w = fmaf(v.x, w.w, a0.w);
         a1.x = fmaf(v.y, w.x, a1.x); a1.y = fmaf(v.y, w.y, a1.y); a1.z = fmaf(v.y, w.z, a1.z); a1.w = fmaf(v.y, w.w, a1.w);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         for (int j = lane; j < H; j += 32) {
           const float pre = nhs[b * ldw + j];
           h0 += softplusf_(pre);
-          h1 += softplusf_(pre + d * ld_remote1(Ws + lr_ * ldw + j, owner));
+          h1 += softplusf_(pre + d * ld_remote1(Ws + lr_ * lds + j, owner));
         }
         h0 = warp_sum(h0);
         h1 = warp_sum(h1);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       for (int it = tid; it < rows * nb4; it += NT) {
         const int r = it % rows, b4 = it / rows;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* wr = Ws + r * ldw;
+        const float* wr = Ws + r * lds;
         const float* h0p = hs + (4 * b4) * ldw;
 #pragma unroll 2
         for (int q = 0; q < CQ; ++q) {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         gs[2] = fmaf(a, ph4.z, gs[2]); gs[2] = fmaf(-n, nh4.z, gs[2]);
         gs[3] = fmaf(a, ph4.w, gs[3]); gs[3] = fmaf(-n, nh4.w, gs[3]);
       }
-      float4 w4 = *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q), s4 = *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q);
+      float4 w4 = *reinterpret_cast<float4*>(Ws + r * lds + 4 * q), s4 = *reinterpret_cast<float4*>(Ss + r * lds + 4 * q);
       float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.wc != 0.f) n4 = __ldg(reinterpret_cast<const float4*>(p.Wsnap + (size_t)(row0 + r) * ldw + 4 * q));
       float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, nv4[4] = {n4.x, n4.y, n4.z, n4.w};
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         wo[c] = 4 * q + c < H ? wv[c] * mult + sv[c] * p.lr : wv[c];    // :364 (OLD speed); padding columns stay zero
         if (4 * q + c >= H) so[c] = sv[c];
       }
-      *reinterpret_cast<float4*>(Ws + r * ldw + 4 * q) = make_float4(wo[0], wo[1], wo[2], wo[3]);
-      *reinterpret_cast<float4*>(Ss + r * ldw + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
+      *reinterpret_cast<float4*>(Ws + r * lds + 4 * q) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+      *reinterpret_cast<float4*>(Ss + r * lds + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
     }
     for (int r = tid; r < rows; r += NT) {                       // visible bias  src/rbm.py:417
       float gsum = 0.f;
@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
   // ---- write the resident state back ----
   for (int e = tid; e < rows * CQ; e += NT) {
     const int r = e / CQ, q = e - r * CQ;
-    *reinterpret_cast<float4*>(p.W + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ws + r * ldw + 4 * q);
-    *reinterpret_cast<float4*>(p.S + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ss + r * ldw + 4 * q);
+    *reinterpret_cast<float4*>(p.W + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ws + r * lds + 4 * q);
+    *reinterpret_cast<float4*>(p.S + (size_t)(row0 + r) * ldw + 4 * q) = *reinterpret_cast<const float4*>(Ss + r * lds + 4 * q);
   }
   for (int r = tid; r < rows; r += NT) {
     p.vb[row0 + r] = vbs[r];
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
 }
 
 struct Geometry {
-  int BTS, CQ, rows_per_cta, rows_alloc, G;
+  int BTS, CQ, rows_per_cta, rows_alloc, G, lds;
   int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
       off_misc;
   size_t smem;
@@ -474,7 +474,8 @@ static Geometry plan(const mdbn_cd_args& a) {
   g.rows_alloc = (g.rows_per_cta + 3) & ~3;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~(size_t)127; return (int)o; };
-  const size_t slab = (size_t)g.rows_alloc * a.ldw * 4, vis = (size_t)g.rows_alloc * g.BTS * 4,
+  g.lds = ((a.ldw / 4) & 1) ? a.ldw : a.ldw + 4;
+  const size_t slab = (size_t)g.rows_alloc * g.lds * 4, vis = (size_t)g.rows_alloc * g.BTS * 4,
                hid = (size_t)g.BTS * a.ldw * 4;
   g.G = NT / (g.CQ * (g.BTS / 4));
   g.G = g.G < 1 ? 1 : (g.G > 8 ? 8 : g.G);
@@ -524,7 +525,7 @@ int tiny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t 
   p.c2 = (uint32_t)a.rng.offset; p.c3 = (uint32_t)(a.rng.offset >> 32);
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
-  p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.BTS = g.BTS; p.CQ = g.CQ; p.G = g.G;
+  p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.BTS = g.BTS; p.CQ = g.CQ; p.G = g.G; p.lds = g.lds;
   p.off_park = g.off_park;
   p.off_W = g.off_W; p.off_S = g.off_S; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vin = g.off_vin;
   p.off_hs = g.off_hs; p.off_pc = g.off_pc; p.off_ph = g.off_ph; p.off_nh = g.off_nh; p.off_part = g.off_part;
