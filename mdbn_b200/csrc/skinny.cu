@@ -15,12 +15,15 @@
 //   * pass 1..k   : FUSED propdown + propup from the SAME staged tile: v_i = h . W[i,:] is
 //     complete inside the owning CTA, its bias/sigmoid/Bernoulli epilogue runs in place and the tile is
 //     immediately reused for  h' += v_i W[i,:];  a Gibbs step reads W once, not twice;
-//   * hidden pre-activations need all rows: per-CTA partials -> global scratch -> grid
-//     barrier -> each CTA reduces a slice in fixed order (deterministic) + bias + sigmoid +
-//     sample -> grid barrier -> every CTA reloads the full [B,H] hidden state;
+//   * hidden pre-activations need all rows: ONE grid barrier per pass.  Every CTA adds its [B,H] partial to a
+//     fixed-point (2^-32, int64) accumulator in L2 with red.global.add.u64 (integer sums commute: the result is
+//     bitwise reproducible), arrives at the barrier, and afterwards rebuilds the whole chain state itself
+//     (bias, sigmoid, element-indexed Philox draw) in compact loops over shared memory;
 //   * last pass  : statistics + lambda_1/lambda_2/momentum update fused: W and W_speed tiles
 //     are read once and written once; v0 and nv slabs never left shared memory.
-// All arithmetic is plain fp32 FFMA.  HBM traffic per step: (k+1) reads of W + read W,S + write W,S
+// Several steps can be chained in one launch (n_steps, CHAIN instantiation): a CTA only ever reads its own rows
+// of W / W_speed / vb, everything that crosses CTAs is ordered by the barriers of the next step.
+// All arithmetic is plain fp32 FFMA / FFMA2.  HBM traffic per step: (k+1) reads of W + read W,S + write W,S
 // (+ read W_snap) versus the (2k+1)+4 of an unfused implementation.
 #include <cuda.h>
 #include <stdlib.h>
