@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
     }
   };
   mark();
+  if (p.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[32 + cta] = t; }
 
   if (tid == 0) {
     for (int i = 0; i < MAX_SLOTS; ++i) mbar_init(&bars[i], 1);
@@ -959,6 +960,7 @@ __global__ void __launch_bounds__(NT, 1) cd_skinny_kernel(const __grid_constant_
 
   // reset the barrier for the next launch: the last CTA out switches off the lights
   __syncthreads();
+  if (p.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[32 + 256 + cta] = t; }
   if (tid == 0) {
     __threadfence();
     const unsigned long long prev = atomicAdd(p.bar + 1, 1ULL);
@@ -1168,6 +1170,16 @@ int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_
     fprintf(stderr, "[skinny timeline us] V=%d H=%d B=%d k=%d R=%d nslots=%d:", a.V, a.H, a.B, a.k, g.R, g.nslots);
     for (int i = 1; i < 13; ++i) fprintf(stderr, " %.1f", (double)(t[i] - t[0]) * 1e-3);
     fprintf(stderr, "\n");
+    {
+      static unsigned long long se[512];
+      MDBN_CUDA(cudaMemcpy(se, p.dbg + 32, (256 + g.grid) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      double smin = 1e30, smax = -1e30, emin = 1e30, emax = -1e30;
+      for (int i = 0; i < g.grid; ++i) {
+        const double s0 = (double)((long long)(se[i] - t[0])) * 1e-3, e0 = (double)((long long)(se[256 + i] - t[0])) * 1e-3;
+        smin = s0 < smin ? s0 : smin; smax = s0 > smax ? s0 : smax; emin = e0 < emin ? e0 : emin; emax = e0 > emax ? e0 : emax;
+      }
+      fprintf(stderr, "[skinny cta spread us] start %.1f..%.1f  end %.1f..%.1f\n", smin, smax, emin, emax);
+    }
   }
   return rc;
 }
