@@ -39,6 +39,8 @@ struct Params {
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
   int rows_per_cta, rows_alloc, BTS, CQ, G, lds;
+  int use_m;                 // GRBM with k > 1: Gibbs steps 0..k-2 run on M = W^T W (see below)
+  int off_M, off_Mp;
   unsigned long long* dbg;   // optional phase timeline (MDBN_TINY_TIMING=1), rank 0, first step
   // shared-memory byte offsets
   int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb,
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
   float* svbs = reinterpret_cast<float*>(smem + p.off_svb);   // [rows_alloc]
   float* hbs = reinterpret_cast<float*>(smem + p.off_hb);     // [ldw]
   float* shbs = reinterpret_cast<float*>(smem + p.off_shb);   // [ldw]
+  float* Ms = reinterpret_cast<float*>(smem + p.off_M);       // [H+1][ldw]  W^T W of ALL rows; row H = vb . W
+  float* Mp = reinterpret_cast<float*>(smem + p.off_Mp);      // [H+1][ldw]  this CTA's share of it
   float* park = reinterpret_cast<float*>(smem + p.off_park);  // [G][BTS][ldw] row-group partials of a propup
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, [40] cost partial, [48..] sidx
 
@@ -240,9 +244,42 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       float* my = part + (size_t)parity * 2 * nhid;
       up_partial(v0s, my);
       if (p.pcd) up_partial(nvs, my + nhid);
+      if (p.use_m) {
+        // Gaussian visibles are mean-field (src/rbm.py:669): v = h W^T + vb feeds the next propup unsampled, so
+        //   pre_h' = (h W^T + vb) W + hb = h (W^T W) + (vb W + hb).
+        // With k > 1 the first k-1 Gibbs steps therefore run on the H x H matrix M = W^T W, locally in every
+        // CTA and without any exchange; only the last step (whose visible means enter the statistics) goes
+        // through the V visibles.  M does not depend on the minibatch: its partial over the owned rows is
+        // exchanged behind the same cluster barrier as the positive phase.
+        for (int it = tid; it < (H + 1) * CQ; it += NT) {
+          const int i = it / CQ, q = it - i * CQ;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* col = i < H ? Ws + i : vbs;          // column i of the slab, or the visible bias (row H)
+          const int cs = i < H ? lds : 1;
+#pragma unroll 8
+          for (int r = 0; r < rows; ++r) {
+            const float wi = col[r * cs];
+            const float4 w4 = *reinterpret_cast<const float4*>(Ws + r * lds + 4 * q);
+            a.x = fmaf(wi, w4.x, a.x); a.y = fmaf(wi, w4.y, a.y); a.z = fmaf(wi, w4.z, a.z); a.w = fmaf(wi, w4.w, a.w);
+          }
+          *reinterpret_cast<float4*>(Mp + i * ldw + 4 * q) = a;
+        }
+      }
       mark();
       cluster_sync();
       mark();
+      if (p.use_m) {
+        for (int it = tid; it < (H + 1) * CQ; it += NT) {
+          const float* lp = Mp + 4 * it + (it / CQ) * (ldw - 4 * CQ);
+          float4 sm = ld_remote4(lp, 0);
+#pragma unroll
+          for (uint32_t c = 1; c < CL; ++c) {
+            const float4 o = ld_remote4(lp, c);
+            sm.x += o.x; sm.y += o.y; sm.z += o.z; sm.w += o.w;
+          }
+          *reinterpret_cast<float4*>(Ms + (lp - Mp)) = sm;
+        }
+      }
       const RngSeg rs0 = seg(0, 0, step);
       all_reduce(my, [&](int b, int j0, const float (&pre)[4]) {
         const float mean[4] = {sigmoid_fast_(pre[0]), sigmoid_fast_(pre[1]), sigmoid_fast_(pre[2]), sigmoid_fast_(pre[3])};
@@ -303,6 +340,30 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
       const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s, step);
       const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
+      if (p.use_m && !last) {
+        // h' ~ sigmoid(h M + vb W + hb): every CTA for the whole [B, H], no exchange (B * CQ <= NT)
+        float smp[4] = {0.f, 0.f, 0.f, 0.f};
+        const int b = tid / CQ, q = tid - b * CQ;
+        const bool mine = tid < B * CQ;
+        if (mine) {
+          const float4 c4 = *reinterpret_cast<const float4*>(Ms + H * ldw + 4 * q);
+          const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * q);
+          float4 a = make_float4(c4.x + hb4.x, c4.y + hb4.y, c4.z + hb4.z, c4.w + hb4.w);
+          const float* hrow = hs + b * ldw;
+#pragma unroll 8
+          for (int i = 0; i < H; ++i) {
+            const float hv = hrow[i];
+            const float4 m4 = *reinterpret_cast<const float4*>(Ms + i * ldw + 4 * q);
+            a.x = fmaf(hv, m4.x, a.x); a.y = fmaf(hv, m4.y, a.y); a.z = fmaf(hv, m4.z, a.z); a.w = fmaf(hv, m4.w, a.w);
+          }
+          const float mean[4] = {sigmoid_fast_(a.x), sigmoid_fast_(a.y), sigmoid_fast_(a.z), sigmoid_fast_(a.w)};
+          sample4(rs_h, b, 4 * q, mean, smp);
+        }
+        __syncthreads();
+        if (mine) *reinterpret_cast<float4*>(hs + b * ldw + 4 * q) = make_float4(smp[0], smp[1], smp[2], smp[3]);
+        __syncthreads();
+        continue;
+      }
       // propdown of the owned rows (complete dot products: every CTA holds the whole chain state) + epilogue
       const int nb4 = BTS >> 2;
       for (int it = tid; it < rows * nb4; it += NT) {
@@ -456,8 +517,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
 }
 
 struct Geometry {
-  int BTS, CQ, rows_per_cta, rows_alloc, G, lds;
-  int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
+  int BTS, CQ, rows_per_cta, rows_alloc, G, lds, use_m;
+  int off_M, off_Mp, off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
       off_misc;
   size_t smem;
   bool ok;
@@ -480,6 +541,9 @@ static Geometry plan(const mdbn_cd_args& a) {
   g.G = NT / (g.CQ * (g.BTS / 4));
   g.G = g.G < 1 ? 1 : (g.G > 8 ? 8 : g.G);
   while (g.G > 1 && (size_t)g.G * hid > 48 * 1024) --g.G;
+  g.use_m = a.kind == MDBN_GRBM && a.k > 1 && a.ldw <= 64 && a.B * g.CQ <= NT;
+  g.off_M = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
+  g.off_Mp = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
   g.off_park = take(g.G > 1 ? (size_t)g.G * hid : 0);
   g.off_W = take(slab); g.off_S = take(slab);
   g.off_v0 = take(vis); g.off_nv = take(vis); g.off_vin = take(vis);
@@ -526,6 +590,7 @@ int tiny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t 
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
   p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.BTS = g.BTS; p.CQ = g.CQ; p.G = g.G; p.lds = g.lds;
+  p.use_m = g.use_m; p.off_M = g.off_M; p.off_Mp = g.off_Mp;
   p.off_park = g.off_park;
   p.off_W = g.off_W; p.off_S = g.off_S; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vin = g.off_vin;
   p.off_hs = g.off_hs; p.off_pc = g.off_pc; p.off_ph = g.off_ph; p.off_nh = g.off_nh; p.off_part = g.off_part;
