@@ -26,6 +26,8 @@ typedef struct mdbn_ctx mdbn_ctx;
 
 enum { MDBN_RBM = 0, MDBN_GRBM = 1 };                       /* src/rbm.py:46 / :631 */
 enum { MDBN_RNG_NONE = 0, MDBN_RNG_BUFFER = 1, MDBN_RNG_PHILOX = 2 };
+/* AUTO picks by shape (full steps): TINY (one cluster, weights in shared memory: small layers), SKINNY (persistent
+ * grid kernel, B <= 20), TENSOR (tcgen05 TF32 GEMMs, B % 32 == 0, needs tf32 = 1), else GENERIC (fp32 SIMT). */
 enum { MDBN_PATH_AUTO = 0, MDBN_PATH_GENERIC = 1, MDBN_PATH_SKINNY = 2, MDBN_PATH_TENSOR = 3, MDBN_PATH_TINY = 4 };
 enum { MDBN_PHASE_FULL = 0, MDBN_PHASE_STATS = 1, MDBN_PHASE_APPLY = 2 };
 

@@ -405,6 +405,24 @@ class RBM(object):
         pre_v, v_mean, v_sample = self.sample_v_given_h(h_sample, u=u_v)
         return [pre_h, h_mean, h_sample, pre_v, v_mean, v_sample]
 
+    def make_sample_fn(self, persistent_vis_chain, plot_every=500):
+        """The `sample_fn` of the reference's sampling demo (src/rbm.py:806-853): every call runs `plot_every`
+        steps of `gibbs_vhv` on the persistent visible chains [n_chains, V] (a Shared, updated in place with
+        the last visible sample) and returns (vis_mf, vis_sample) of the last step as numpy arrays.
+        Works for GRBM as well (its gibbs_vhv feeds the hidden MEAN down, src/rbm.py:673-682)."""
+        chain = persistent_vis_chain if isinstance(persistent_vis_chain, Shared) else \
+            Shared(persistent_vis_chain, name='persistent_vis_chain', device=self.device)
+
+        def sample_fn():
+            v = chain.data
+            v_mean = v
+            for _ in range(int(plot_every)):
+                _, _, _, _, v_mean, v = self.gibbs_vhv(v)
+            chain.data.copy_(v)
+            return v_mean.cpu().numpy(), v.cpu().numpy()
+        sample_fn.chain = chain
+        return sample_fn
+
     def get_cost_updates(self, lr=0.1, k=1, lambda_1=0.0, lambda_2=0.0, weightcost=0.0,
                          batch_size=None, persistent=None, symbolic_grad=False):
         """One step of CD-k / PCD-k (src/rbm.py:258-376).  Returns (cost, updates): `updates`

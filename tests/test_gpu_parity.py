@@ -572,3 +572,27 @@ def test_skinny_tc_opt_in_subprocess():
                         "-k", "config_shapes and auto"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+# ---------------------------------------------------------------------------
+# 8f-4: the sampling demo's persistent gibbs_vhv chains (src/rbm.py:806-853)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [O.RBM, O.GRBM])
+def test_sample_fn_runs_persistent_vhv_chains(kind):
+    m = M()
+    V, H, n_chains, plot_every = 120, 40, 6, 7
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(2), V, H).astype(np.float32)
+    start = synth(kind, n_chains, V, seed=8)
+    a = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(3))
+    b = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(3))
+    fn = a.make_sample_fn(m.shared(start), plot_every=plot_every)
+    v = torch.from_numpy(start).to(b.device)
+    for call in range(2):
+        mf, smp = fn()
+        for _ in range(plot_every):
+            _, _, _, _, v_mean, v = b.gibbs_vhv(v)
+        assert np.array_equal(mf, v_mean.cpu().numpy()) and np.array_equal(smp, v.cpu().numpy())
+        assert np.array_equal(fn.chain.get_value(), smp)                  # the chain persists between calls
+    if kind == O.RBM:
+        assert set(np.unique(smp)) <= {0.0, 1.0}
