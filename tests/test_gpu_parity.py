@@ -596,3 +596,48 @@ def test_sample_fn_runs_persistent_vhv_chains(kind):
         assert np.array_equal(fn.chain.get_value(), smp)                  # the chain persists between calls
     if kind == O.RBM:
         assert set(np.unique(smp)) <= {0.0, 1.0}
+
+
+# ---------------------------------------------------------------------------
+# the small layers are served by the cluster kernel under "auto": keep the grid kernel covered on them too
+# (k = 10 exercises the rotation / re-zeroing of its three Gibbs accumulators), and the cluster kernel on
+# every configuration it accepts
+# ---------------------------------------------------------------------------
+SMALL_CFGS = [c for c in CONFIG_SHAPES if c[0] in ("cfg4_me_cd10", "cfg4_top_cd1", "cfg4_top2_cd1")] + [
+    ("me_pcd10_b10", O.GRBM, 559, 40, 10, 10, True, 0.005, 0.0, 0.01, 0.01, 0.0),
+    ("rbm_400x40_cd5", O.RBM, 400, 40, 20, 5, False, 0.1, 0.6, 0.0, 0.0, 0.0002)]
+
+
+@pytest.mark.parametrize("path", ["skinny", "tiny"])
+@pytest.mark.parametrize("cfg", SMALL_CFGS, ids=[c[0] for c in SMALL_CFGS])
+def test_small_layers_both_kernels(cfg, path):
+    test_config_shapes_vs_oracle(cfg, path)
+
+
+@pytest.mark.parametrize("path,kind,pcd,k", [("skinny", O.GRBM, True, 4), ("skinny", O.RBM, False, 5),
+                                             ("tiny", O.GRBM, False, 4), ("tiny", O.RBM, True, 2)])
+def test_run_steps_deep_chains_both_kernels(path, kind, pcd, k):
+    """Chained launches with k > 3 (the grid kernel re-zeroes and rotates its Gibbs accumulators inside a step and
+    alternates the accumulator sets between the steps of one launch) == single-step launches, bitwise."""
+    m = M()
+    V, H, B, n = 640, 56, 10, 6
+    data = synth(kind, B * n, V, seed=17)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(6), V, H).astype(np.float32)
+
+    def make():
+        r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(11))
+        P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+        cost, upd = r.get_cost_updates(lr=0.02, k=k, lambda_1=0.01, lambda_2=0.1, weightcost=0.0002, batch_size=B,
+                                       persistent=P)
+        return r, r.make_train_fn(data, cost, upd, path=path), P
+    idx = np.arange(B * n, dtype=np.int32).reshape(n, B)
+    r1, f1, P1 = make()
+    single = [f1(idx[s], 0.5) for s in range(n)]
+    r2, f2, P2 = make()
+    chained = f2.run_steps(idx[:4], 0.5) + f2.run_steps(idx[4:], 0.5)
+    assert single == chained
+    for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        assert np.array_equal(getattr(r1, name).get_value(), getattr(r2, name).get_value()), name
+    if pcd:
+        assert np.array_equal(P1.get_value(), P2.get_value())
