@@ -6,6 +6,7 @@ reference so that its notebooks can read runs produced here and vice versa.
   import_TCGA_data / load_n_preprocess_data   src/utils.py:34-52, :77-119
   find_unique_classes / remap_class           src/utils.py:124-177
   save_network / load_network                 src/AMLsm.py:112-205 (+ DBN(W_list=, b_list=), src/dbn.py:154-166)
+  MNIST (idx loader, normalize, tilings)      src/MNIST.py:33-124 (the sampling demo's data and pictures)
 """
 import gzip
 import os
@@ -171,3 +172,64 @@ def load_network(input_file, input_folder='.', dbn_factory=None):
             kw['gauss'] = False
         built[name] = dbn_factory(**kw)
     return built.get('me'), built.get('ge'), built.get('sm'), built.get('dm'), built.get('top')
+
+
+# --------------------------------------------------------------------------- the demo's data set and pictures
+class MNIST(object):
+    """src/MNIST.py:33-124: idx-format images and labels (gzip), the guideTR 13.2 normalisation and the two image
+    tilings of the RBM demo.  The files must already be in `datadir` (the reference downloads them; no network
+    here).  Attributes as in the reference: images [n, sizeY*sizeX], labels [n, 1], n_levels, sizeX, sizeY."""
+
+    def __init__(self, datafile='train-images-idx3-ubyte.gz', targetfile='train-labels-idx1-ubyte.gz', datadir='data',
+                 dtype='float32'):
+        self.dtype = dtype
+        self.n_images = self.load(datafile, targetfile, datadir)
+
+    def load(self, datafile, targetfile, datadir):
+        import struct
+        for f in (datafile, targetfile):
+            if not os.path.isfile(os.path.join(datadir, f)):
+                raise IOError("%s is not in %s (fetch it from http://yann.lecun.com/exdb/mnist)" % (f, datadir))
+        with gzip.open(os.path.join(datadir, datafile), 'rb') as f:
+            raw = f.read()
+        _, n_images, self.sizeY, self.sizeX = struct.unpack(">IIII", raw[:16])
+        size = self.sizeY * self.sizeX
+        self.images = numpy.frombuffer(raw, dtype=numpy.uint8, count=n_images * size, offset=16) \
+            .reshape(n_images, size).astype(self.dtype)
+        with gzip.open(os.path.join(datadir, targetfile), 'rb') as f:
+            raw = f.read()
+        _, n_labels = struct.unpack(">II", raw[:8])
+        self.labels = numpy.frombuffer(raw, dtype=numpy.uint8, count=n_labels, offset=8) \
+            .reshape(n_labels, 1).astype(self.dtype)
+        self.n_levels = int(self.labels.max() - self.labels.min() + 1)
+        return n_images
+
+    def normalize(self, X):
+        """Zero mean, about unit deviation: (X - 128) / 128 over the GLOBAL standard deviation (:90-96)."""
+        X = (X - 128.0) / 128.0
+        return X / numpy.std(X)
+
+    def _tile(self, rows_of_images):
+        gap_r, gap_c = self.sizeY + 1, self.sizeX + 1
+        Y = numpy.zeros((len(rows_of_images) * gap_r, max(len(r) for r in rows_of_images) * gap_c), dtype=self.dtype)
+        for r, row in enumerate(rows_of_images):
+            for c, img in enumerate(row):
+                Y[r * gap_r:(r + 1) * gap_r - 1, c * gap_c:(c + 1) * gap_c - 1] = \
+                    numpy.asarray(img).reshape(self.sizeX, self.sizeY)          # (sic: X before Y, :108)
+        return Y
+
+    def display_weigths(self, X, n_hidden):
+        """One tile per hidden unit on a round(sqrt(n_hidden))-wide square grid (:98-111; the reference's
+        spelling; units that do not fit the square are not drawn, a short last row stays black)."""
+        W = numpy.asarray(X).T
+        n = int(numpy.round(numpy.sqrt(n_hidden)))
+        rows = [[W[r * n + c] for c in range(n) if r * n + c < n_hidden] for r in range(n)]
+        Y = self._tile([r for r in rows if r] or [[]])
+        full = numpy.zeros((n * (self.sizeY + 1), n * (self.sizeX + 1)), dtype=self.dtype)
+        full[:Y.shape[0], :Y.shape[1]] = Y
+        return full
+
+    def display_samples(self, samples):
+        """One row of tiles per sampling round, one column per chain (:113-122)."""
+        return self._tile([list(s) for s in samples])
+

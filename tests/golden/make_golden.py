@@ -368,6 +368,36 @@ def io_case():
             np.load = np_load
         out["ckpt_roundtrip_ok"] = np.array([np.array_equal(a.get_value(), b.get_value())
                                              for a, b in zip(ge.params + top.params, ge2.params + top2.params)])
+        # MNIST idx loader / normalisation / tilings of the demo (src/MNIST.py is Python 2: give it xrange,
+        # numpy.int and the float type it asks theano for)
+        import gzip, struct
+        import MNIST as ref_mnist
+        ref_mnist.xrange = range
+        if not hasattr(np, "int"):
+            np.int = int
+        nimg, sy, sx = 7, 4, 4      # square, like MNIST: the reference reshapes to (sizeX, sizeY) into a (sizeY, sizeX) slot
+        pix = rs.randint(0, 256, size=(nimg, sy * sx)).astype(np.uint8)
+        lab = np.array([3, 1, 4, 1, 5, 2, 6], dtype=np.uint8)
+        img_bytes = struct.pack(">IIII", 2051, nimg, sy, sx) + pix.tobytes()
+        lab_bytes = struct.pack(">II", 2049, nimg) + lab.tobytes()
+        with gzip.open(os.path.join(tmp, "img.gz"), "wb") as f:
+            f.write(img_bytes)
+        with gzip.open(os.path.join(tmp, "lab.gz"), "wb") as f:
+            f.write(lab_bytes)
+        out["mnist_img_bytes"] = np.frombuffer(img_bytes, dtype=np.uint8)
+        out["mnist_lab_bytes"] = np.frombuffer(lab_bytes, dtype=np.uint8)
+        with redirect_stdout(io.StringIO()):
+            mn = ref_mnist.MNIST("img.gz", "lab.gz", tmp)
+        out["mnist_images"], out["mnist_labels"] = mn.images, mn.labels
+        out["mnist_meta"] = np.array([mn.n_images, mn.sizeY, mn.sizeX, mn.n_levels])
+        out["mnist_norm"] = mn.normalize(mn.images)
+        Wd = rs.randn(sy * sx, 7)
+        out["mnist_W"] = Wd
+        out["mnist_tiles_w7"] = mn.display_weigths(Wd, 7)
+        out["mnist_tiles_w4"] = mn.display_weigths(Wd[:, :4], 4)
+        smp = [[rs.rand(sy * sx) for _ in range(3)] for _ in range(2)]
+        out["mnist_samples"] = np.array(smp)
+        out["mnist_tiles_s"] = mn.display_samples(smp)
     finally:
         shutil.rmtree(tmp)
     np.savez_compressed(os.path.join(HERE, "io_cases.npz"), **out)

@@ -102,3 +102,20 @@ def test_load_network_rebuilds_with_reference_arguments():
     assert (ge["n_ins"], ge["hidden_layers_sizes"], ge["n_outs"]) == (13, [6], 3) and "gauss" not in ge
     assert top["gauss"] is False and len(top["W_list"]) == 2 and len(top["b_list"]) == 2
     assert me["W_list"][0].shape == (9, 4) and sm["b_list"][0].shape == (5,)
+
+
+def test_mnist_loader_and_tilings_match_reference(tmp_path):
+    import gzip
+    with gzip.open(str(tmp_path / "img.gz"), "wb") as f:
+        f.write(G["mnist_img_bytes"].tobytes())
+    with gzip.open(str(tmp_path / "lab.gz"), "wb") as f:
+        f.write(G["mnist_lab_bytes"].tobytes())
+    mn = mio.MNIST("img.gz", "lab.gz", str(tmp_path), dtype="float64")
+    assert [mn.n_images, mn.sizeY, mn.sizeX, mn.n_levels] == G["mnist_meta"].tolist()
+    assert np.array_equal(mn.images, G["mnist_images"]) and np.array_equal(mn.labels, G["mnist_labels"])
+    np.testing.assert_allclose(mn.normalize(mn.images), G["mnist_norm"], rtol=1e-13)
+    assert np.array_equal(mn.display_weigths(G["mnist_W"], 7), G["mnist_tiles_w7"])
+    assert np.array_equal(mn.display_weigths(G["mnist_W"][:, :4], 4), G["mnist_tiles_w4"])
+    assert np.array_equal(mn.display_samples(list(G["mnist_samples"])), G["mnist_tiles_s"])
+    with pytest.raises(IOError):
+        mio.MNIST("missing.gz", "lab.gz", str(tmp_path))
