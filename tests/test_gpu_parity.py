@@ -310,8 +310,9 @@ def test_philox_sampling_statistics_and_determinism():
 
 def test_size_independent_properties_full_size():
     """At BASELINE config-2 size (19937x400): (i) with lr = 0 the parameters do not move but the speeds
-    take the gradient; (ii) STATS over two half-batches sums to STATS over the whole batch (linearity,
-    the data-parallel contract); (iii) a step is deterministic run to run."""
+    take the gradient; (ii) a step is bitwise deterministic run to run.  (Linearity of the statistics — STATS
+    over two half-batches sums to STATS over the whole batch, the data-parallel contract — is
+    test_stats_apply_phases_equal_full_step.)"""
     m = M()
     V, H, B = 19937, 400, 20
     data = synth(O.GRBM, B, V, seed=5)
