@@ -615,13 +615,15 @@ def test_small_layers_both_kernels(cfg, path):
     test_config_shapes_vs_oracle(cfg, path)
 
 
-@pytest.mark.parametrize("path,kind,pcd,k", [("skinny", O.GRBM, True, 4), ("skinny", O.RBM, False, 5),
-                                             ("tiny", O.GRBM, False, 4), ("tiny", O.RBM, True, 2)])
-def test_run_steps_deep_chains_both_kernels(path, kind, pcd, k):
+@pytest.mark.parametrize("path,kind,pcd,k,B", [("skinny", O.GRBM, True, 4, 10), ("skinny", O.RBM, False, 5, 10),
+                                               ("tiny", O.GRBM, False, 4, 10), ("tiny", O.RBM, True, 2, 10),
+                                               ("skinny", O.RBM, True, 2, 20), ("skinny", O.GRBM, False, 1, 17),
+                                               ("tiny", O.GRBM, True, 3, 20)])
+def test_run_steps_deep_chains_both_kernels(path, kind, pcd, k, B):
     """Chained launches with k > 3 (the grid kernel re-zeroes and rotates its Gibbs accumulators inside a step and
     alternates the accumulator sets between the steps of one launch) == single-step launches, bitwise."""
     m = M()
-    V, H, B, n = 640, 56, 10, 6
+    V, H, n = 640, 56, 6
     data = synth(kind, B * n, V, seed=17)
     cls = m.GRBM if kind == O.GRBM else m.RBM
     W0 = O.init_W(np.random.RandomState(6), V, H).astype(np.float32)
