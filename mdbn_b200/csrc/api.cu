@@ -161,7 +161,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   int path = a->path;
   if (path == MDBN_PATH_AUTO) {
     if (a->phase == MDBN_PHASE_FULL && tiny_supported(c, *a)) path = MDBN_PATH_TINY;
-    else if (a->phase == MDBN_PHASE_FULL && (skinny_tc_supported(c, *a) || skinny_supported(c, *a))) path = MDBN_PATH_SKINNY;
+    else if (a->phase == MDBN_PHASE_FULL && skinny_supported(c, *a)) path = MDBN_PATH_SKINNY;
     else if (a->tf32 && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;
     else path = MDBN_PATH_GENERIC;
   }
@@ -169,7 +169,6 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
     case MDBN_PATH_GENERIC:
       return generic_cd_step(c, *a, st);
     case MDBN_PATH_SKINNY:
-      if (skinny_tc_supported(c, *a)) return skinny_tc_cd_step(c, *a, st);     // big layers: tcgen05 edition
       MDBN_CHECK(skinny_supported(c, *a), "cd_step: skinny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B,
                  a->V, a->H, a->ldw, a->phase);
       return skinny_cd_step(c, *a, st);
@@ -198,7 +197,7 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
   const bool want_tiny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_TINY;
   const bool want_skinny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_SKINNY;
   const bool use_tiny = want_tiny && c && a->W && tiny_supported(c, *a);
-  if (use_tiny || (want_skinny && c && a->W && !skinny_tc_supported(c, *a) && skinny_supported(c, *a))) {
+  if (use_tiny || (want_skinny && c && a->W && skinny_supported(c, *a))) {
     MDBN_TRY(check_common(c, a->W, a->ldw, a->B, a->V, a->H));
     MDBN_CHECK(a->kind == MDBN_RBM || a->kind == MDBN_GRBM, "cd_steps: bad kind %d", a->kind);
     MDBN_CHECK(a->hbias && a->vbias && a->W_speed && a->hbias_speed && a->vbias_speed, "cd_steps: NULL parameter/state");

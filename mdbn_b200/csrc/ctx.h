@@ -84,10 +84,6 @@ int skinny_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t 
 bool tiny_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int tiny_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t st);
 
-// ---- skinny persistent path on tcgen05 (B <= 16, H <= 512, large layers): skinny_tc.cu
-bool skinny_tc_supported(const mdbn_ctx*, const mdbn_cd_args& a);
-int skinny_tc_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);
-
 // ---- tcgen05 / TMA path (large batch, TF32): tensor.cu ----------------------
 bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int tensor_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);

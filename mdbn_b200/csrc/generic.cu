@@ -360,7 +360,7 @@ int generic_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   float* HS = (float*)ws_get(c, WS_HS, (size_t)B * H * sizeof(float));
   float* VS = (float*)ws_get(c, WS_VS, (size_t)B * V * sizeof(float));
   float* PREV = (float*)ws_get(c, WS_PREV, (size_t)B * V * sizeof(float));
-  float* RED = (float*)ws_get(c, WS_RED, 4096 * sizeof(float));
+  float* RED = (float*)ws_get(c, WS_RED, (size_t)(B > 4096 ? B : 4096) * sizeof(float));   // pl_row_kernel writes one partial per row
   if (!XV || !YH || !HS || !VS || !PREV || !RED) return 3;
   const bool pcd = a.persistent != nullptr;
   float *XI = nullptr, *PREX = nullptr;

@@ -6,7 +6,7 @@
    [v0^T ph - nv^T nh (V*H) | sum(ph-nh) (H) | sum(v0-nv) (V) | cost numerator | rows]
    per step, after which every rank applies the identical in-place update;
 2. modality parallelism — the per-modality DBNs of an MDBN are independent until their top
-   activations are concatenated (src/AMLsm.py:38-83): one GPU per modality, one gather of
+   activations are concatenated (src/AMLsm.py:38-83): one GPU per modality, one tensor collective of the
    [N, H_top] activations to the rank that trains the joint DBN (src/MDBN.py:31-42).
 
 torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is the plumbing."""
@@ -96,16 +96,22 @@ def train_modalities(specs, rank=None, world=None, group=None, rng_seed=123, bat
             dims = [V] + list(sp["layers_sizes"])
             for a, b in zip(dims[:-1], dims[1:]):
                 rng.uniform(size=(a, b))
-    # one exchange: the small top activations go to rank 0
+    # one exchange: every rank writes the [N, H_top] activations of ITS modalities into their column block of a
+    # zero [N, sum H_top] tensor; a tensor all-reduce(sum) then IS the concatenation (each block has one owner)
+    widths = [int(specs[n]["layers_sizes"][-1]) for n in names]
+    offs = numpy.concatenate([[0], numpy.cumsum(widths)]).astype(int)
+    n_rows = int(specs[names[0]]["data"].shape[0])
     joint = None
     if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, {n: tops[n] for n in tops}, group=group)
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        buf = torch.zeros((n_rows, int(offs[-1])), dtype=torch.float32, device=dev)
+        for i, n in enumerate(names):
+            if n in tops:
+                buf[:, offs[i]:offs[i + 1]] = torch.as_tensor(numpy.asarray(tops[n], dtype=numpy.float32)).to(dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         if rank == 0:
-            allt = {}
-            for g in gathered:
-                allt.update(g)
-            joint = numpy.concatenate([allt[n] for n in names], axis=1)
+            joint = buf.cpu().numpy()
     else:
         joint = numpy.concatenate([tops[n] for n in names], axis=1)
     top_dbn = None

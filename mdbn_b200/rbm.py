@@ -232,6 +232,10 @@ class TrainFn:
             rng, keep = _lib.Rng(_lib.RNG_PHILOX, None, 0, 0), None
         else:
             rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B, n_steps=n_steps)
+            if self.dp is not None and self.dp.world > 1 and rng.mode == _lib.RNG_PHILOX:
+                # data-parallel shards index their draws by the LOCAL row: give every rank its own Philox key so
+                # that row b of two shards never sees the same uniforms (ranks must still agree on the minibatch)
+                rng.seed = (rng.seed ^ (0x9E3779B97F4A7C15 * (self.dp.rank + 1))) & (2 ** 64 - 1)
         a = _lib.CdArgs()
         a.kind, a.noisy = r.kind, int(not getattr(r, "error_free", True))
         a.B, a.B_nom, a.V, a.H, a.k = B, int(h["batch_size"]), r.n_visible, r.n_hidden, int(h["k"])
@@ -295,6 +299,10 @@ class RBM(object):
                               dtype=numpy.float32)
         if not isinstance(W, Shared):
             W = Shared(W, name='W', device=self.device, ld_pad=_PAD)
+        elif W.ld % _PAD != 0:
+            # a user-made shared(W) is dense: move it into row-padded storage IN PLACE so that every holder
+            # of this Shared (weight tying, src/dbn.py:193-202) keeps seeing the same tensor
+            W.repad(_PAD)
         if hbias is None:
             hbias = numpy.zeros(n_hidden, dtype=numpy.float32)
         if not isinstance(hbias, Shared):
@@ -312,7 +320,8 @@ class RBM(object):
         self.momentum = 0.0                                                   # :151
         self.W_speed = Shared(numpy.zeros((n_visible, n_hidden), numpy.float32), name='W_speed',
                               device=self.device, ld_pad=_PAD)               # :153-162
-        assert self.W_speed.ld == self.W.ld, "W and W_speed must share a row stride"
+        if self.W_speed.ld != self.W.ld:
+            raise ValueError("W (row stride %d) and W_speed (%d) must share a row stride" % (self.W.ld, self.W_speed.ld))
         self.hbias_speed = Shared(numpy.zeros(n_hidden, numpy.float32), name='hbias_speed', device=self.device)
         self.vbias_speed = Shared(numpy.zeros(n_visible, numpy.float32), name='vbias_speed', device=self.device)
         self.params_speed = [self.W_speed, self.hbias_speed, self.vbias_speed]

@@ -36,6 +36,17 @@ class Shared:
         self.name = name
         self.version = 0
 
+    def repad(self, ld_pad):
+        """Move a dense 2-D value into storage whose rows are padded to `ld_pad` floats (same object, same value)."""
+        if self.storage.dim() != 2 or self.storage.shape[1] % ld_pad == 0:
+            return
+        t = self.data
+        ld = (t.shape[1] + ld_pad - 1) // ld_pad * ld_pad
+        store = torch.zeros((t.shape[0], ld), dtype=torch.float32, device=t.device)
+        store[:, :t.shape[1]] = t
+        self.storage, self.data = store, store[:, :t.shape[1]]
+        self.version += 1
+
     @property
     def ld(self):
         return self.storage.shape[1] if self.storage.dim() == 2 else 1

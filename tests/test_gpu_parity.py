@@ -159,7 +159,7 @@ CONFIG_SHAPES = [
     ("cfg4_top2_cd1", O.RBM, 24, 3, 20, 1, False, 0.1, 0.9, 0.0, 0.0, 0.0002),
     ("cfg3_dbn_l1", O.RBM, 1000, 1000, 20, 1, False, 0.01, 0.9, 0.0, 0.0, 0.0002),
     ("cfg5_b128_k2", O.RBM, 784, 500, 128, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
-    # large layers with B <= 16 take the tcgen05 edition of the skinny kernel (skinny_tc.cu)
+    # more shapes of the persistent W-streaming kernel (ragged row slabs, narrow and wide layers, odd batches)
     ("tc_ge_cd1_b10", O.GRBM, 19937, 400, 10, 1, False, 0.005, 0.0, 0.01, 0.1, 0.0),
     ("tc_rbm_4096x256_b16_cd2", O.RBM, 4096, 256, 16, 2, False, 0.1, 0.6, 0.0, 0.0, 0.0002),
     ("tc_rbm_2100x512_b8_pcd1", O.RBM, 2100, 512, 8, 1, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
@@ -558,21 +558,6 @@ def test_reference_checkpoint_loads_and_propagates(tmp_path):
     me2, ge2, sm2, _, top2 = m.io.load_network("rt.npz", str(tmp_path), dbn_factory=lambda **kw: m.DBN(verbose=False, **kw))
     for a, b in zip(ge.params + top.params, ge2.params + top2.params):
         assert np.array_equal(a.get_value(), b.get_value())
-
-
-# ---------------------------------------------------------------------------
-# the opt-in tcgen05 edition of the skinny kernel (MDBN_SKINNY_TC=1, csrc/skinny_tc.cu) stays parity-green
-# ---------------------------------------------------------------------------
-def test_skinny_tc_opt_in_subprocess():
-    import subprocess
-    import sys
-    if os.environ.get("MDBN_SKINNY_TC"):
-        pytest.skip("already inside the opt-in run")
-    env = dict(os.environ, MDBN_SKINNY_TC="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
-                        "-k", "config_shapes and auto"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout
 
 
 # ---------------------------------------------------------------------------
