@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmdbn_b200.so")
+# MDBN_B200_LIB: an alternative build of the same library (e.g. the instrumented one of scripts/build_debug.sh)
+LIB_PATH = os.environ.get("MDBN_B200_LIB") or os.path.join(_HERE, "csrc", "libmdbn_b200.so")
 
 RBM, GRBM = 0, 1
 RNG_NONE, RNG_BUFFER, RNG_PHILOX = 0, 1, 2
