@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
   // thread (g, q) owns the SLAB rows r with r mod G == g.  `rem` = (slab row of the tile's first row) mod G, kept
   // incrementally by the tile loops (advance_rem): no division on the tile path
   auto first_row = [&](int rem) { return g >= rem ? g - rem : g - rem + p.G; };
-  auto advance_rem = [&](int& rem, int step_rows) { rem += step_rows; while (rem >= p.G) rem -= p.G; };
+  const int remR = R % p.G, rem8 = 8 % p.G, rem16 = 16 % p.G;     // tile heights mod G
+  auto advance_rem = [&](int& rem, int step_mod) { rem += step_mod; if (rem >= p.G) rem -= p.G; };
   auto up_tile = [&](const unsigned char* __restrict__ tile, const float* __restrict__ src,
                      const float* __restrict__ src2, int rem, int nr, P2 (&acc)[BTP / 2][4],
                      P2 (&acc2)[BTP / 2][4], bool dual) {
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
       const unsigned char* tile = smem + (size_t)st * p.slot_bytes;
       const int nr = min(R, rows - j * R);
       if (!(F & 1)) up_tile(tile, v0s + (size_t)j * R * BTS, nvs + (size_t)j * R * BTS, rem, nr, acc, acc2, p.pcd != 0);
-      advance_rem(rem, R);
+      advance_rem(rem, remR);
       __syncthreads();
       if (!(F & 2)) issue(j + depth, depth);
     }
@@ -783,27 +784,34 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
       if (!(F & 4)) {
         if (R == 32) {
           const int lr = lane & 15, half = lane >> 4;
-          float da[BT], db[BT];
+          // packed FMAs: an accumulator pair holds the partial sums over the even and the odd columns of a row
+          P2 da2[BT], db2[BT];
 #pragma unroll
-          for (int b = 0; b < BT; ++b) da[b] = db[b] = 0.f;
-          for (int bx = warp * 2 + half; bx < nbox; bx += NWARP * 2) {
-            const unsigned char* bpa = tile + bx * box_bytes + lr * 128;
-            const float* hb0 = hs + bx * 32;
+          for (int b = 0; b < BT; ++b) da2[b] = db2[b] = 0ULL;
+          const uint32_t s_hs = smem_u32(hs);
+          // a warp takes whole boxes; its half-warps take ADJACENT 16-byte chunks of a box, so the two h addresses of
+          // a broadcast load fall into one 128-byte line (one wavefront; different boxes would conflict: two)
+          for (int bx = warp; bx < nbox; bx += NWARP) {
+            const uint32_t bpa = smem_u32(tile) + bx * box_bytes + lr * 128;
+            const uint32_t hb0 = s_hs + bx * 128;
             // NOT fully unrolled: a box is visited once per tile, straight-line code this long is bound by
             // instruction fetch (ncu: stall_no_instruction); the 2-chunk body is re-run from the i-cache
 #pragma unroll 2
-            for (int c = 0; c < 8; ++c) {
-              const int sw = (c ^ (lr & 7)) << 4;                                  // rows l and l+16 swizzle alike
-              const float4 wa = *reinterpret_cast<const float4*>(bpa + sw);
-              const float4 wb = *reinterpret_cast<const float4*>(bpa + 16 * 128 + sw);
+            for (int c2 = 0; c2 < 4; ++c2) {
+              const int c = 2 * c2 + half;
+              const uint32_t sw = (c ^ (lr & 7)) << 4;                             // rows l and l+16 swizzle alike
+              const ulonglong2 wa = lds128(bpa + sw), wb = lds128(bpa + 16 * 128 + sw);
 #pragma unroll
               for (int b = 0; b < BT; ++b) {
-                const float4 h4 = *reinterpret_cast<const float4*>(hb0 + b * ldh + c * 4);   // broadcast per half-warp
-                da[b] = fmaf(h4.x, wa.x, fmaf(h4.y, wa.y, fmaf(h4.z, wa.z, fmaf(h4.w, wa.w, da[b]))));
-                db[b] = fmaf(h4.x, wb.x, fmaf(h4.y, wb.y, fmaf(h4.z, wb.z, fmaf(h4.w, wb.w, db[b]))));
+                const ulonglong2 h4 = lds128(hb0 + (b * ldh + c * 4) * 4);          // broadcast per half-warp
+                da2[b] = ffma2(h4.x, wa.x, ffma2(h4.y, wa.y, da2[b]));
+                db2[b] = ffma2(h4.x, wb.x, ffma2(h4.y, wb.y, db2[b]));
               }
             }
           }
+          float da[BT], db[BT];
+#pragma unroll
+          for (int b = 0; b < BT; ++b) { da[b] = lo2(da2[b]) + hi2(da2[b]); db[b] = lo2(db2[b]) + hi2(db2[b]); }
           // the two half-warps hold partials of the same 32 rows: add them, lanes 0-15 store both rows
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
@@ -869,11 +877,18 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
       __syncthreads();
       // ---- propup accumulation from the same tile ----
       if (!(F & 16)) up_tile(tile, vt, vt, rem, nr, acc, acc, false);
-      advance_rem(rem, R);
+      advance_rem(rem, remR);
       __syncthreads();
       if (!(F & 32)) issue(j + depth, depth);
     }
     if (last) mark();   // Gibbs tiles done
+    if (last && fuse_next) {
+      // the gather of the next minibatch has long landed: round(v0) for its pseudo-likelihood sums (the block
+      // barriers of the flush below publish both slabs to the statistics pass)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      if (p.pcd) for (int e = tid; e < rows * BTS; e += NT) xn[e] = roundf(v0n[e]);     // src/rbm.py:428
+    }
     // accumulator of step s+1 was last used by step s-2 of THIS launch: everybody finished reading it before
     // the previous barrier, nobody adds to it before the next one
     if (s >= 2 && s + 1 < p.k) {
@@ -898,23 +913,17 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
 
   // =============================== statistics + update (+ positive phase of the next step) =======================
   {
-    // short tiles (8 rows) for this pass: it streams 2-3 arrays and wants a deep pipeline
+    // short tiles for this pass: it streams 2-3 arrays and wants a deep pipeline (16 rows when three stages of
+    // them fit: half as many tile barriers, else 8)
     const int narr = p.wc != 0.f ? 3 : 2;
-    const int TRS = 8, slot_s = (TRS * ldw * 4 + 127) & ~127;
+    const int TRS = (p.nslots * p.slot_bytes) / (narr * ((16 * ldw * 4 + 127) & ~127)) >= 3 ? 16 : 8;
+    const int slot_s = (TRS * ldw * 4 + 127) & ~127;
     int depth = (p.nslots * p.slot_bytes) / (narr * slot_s);
     depth = depth > MAX_SLOTS ? MAX_SLOTS : depth;
     const int ntiles_s = (rows + TRS - 1) / TRS;
     if (warp == 0) for (int j = 0; j < depth; ++j) issue_rows(j, narr, depth, TRS, slot_s);
     const int ldw4x = ldw >> 2;
     // next minibatch (FUSE): the cp.async gather has long landed; round(v0) for the pseudo-likelihood sums
-    if (fuse_next) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncthreads();
-      if (p.pcd) {
-        for (int e = tid; e < rows * BTS; e += NT) xn[e] = roundf(v0n[e]);     // src/rbm.py:428
-        __syncthreads();
-      }
-    }
     // hidden means of the minibatch rows b and b+1 of one column travel as a pair: packed FFMA2 with the
     // (v[b], v[b+1]) pairs of the slabs, even and odd rows summed at the end -> 8 independent chains of BT/2
     P2 ph2[BT / 2][4], nh2[BT / 2][4];      // nh2 holds -nh: one packed add joins the two chains
@@ -1098,7 +1107,7 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
             }
           }
         }
-        advance_rem(rem, TRS);
+        advance_rem(rem, TRS == 16 ? rem16 : rem8);
         const long long c1 = p.dbg ? clock64() : 0;
         __syncthreads();
         if (p.dbg) t_sync += clock64() - c1;
