@@ -11,9 +11,13 @@ gene-expression shape), PCD-1, batch 10, on synthetic z-scored data [170,19937].
 With N>1 every rank trains its own layer of that shape (the path shards by independent
 layers/modalities; no data-path collective) -> weak scaling.
 
-Timing hygiene: W >= 3 warm-up steps; the timed steps rotate over 4 independent parameter sets
-(4 x (W + W_speed) = 255 MB > the 126 MB L2) so every step streams its weights from HBM; CUDA
-events on the launching stream; barrier + synchronize on both sides; max over ranks.
+The timed region issues what the reference's training loops issue through this package (DBN.training /
+RBM.learn_model -> TrainFn.run_steps): the minibatches of an epoch in ONE launch (mdbn_cd_steps).  Between
+launches the parameter sets rotate over 4 independent layers (4 x (W + W_speed) = 255 MB > the 126 MB L2),
+so every launch starts with its weights in HBM; `single_launch` is the same step as one launch per minibatch.
+
+Timing hygiene: W >= 3 warm-up steps; CUDA events on the launching stream; barrier + synchronize on both
+sides (a ~1 ms spin kernel in front of the first event absorbs the host's enqueue latency); max over ranks.
 """
 import argparse
 import json
@@ -143,14 +147,32 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def config_of(wname, w):
+    """The workload description — byte-identical in both arms (b200 and --impl reference)."""
+    return {"workload": wname, "layer": "%s %d->%d" % ("GRBM" if w["kind"] else "RBM", w["V"], w["H"]),
+            "batch": w["B"], "k": w["k"], "pcd": bool(w["pcd"])}
+
+
+def host_threads():
+    """All host cores for the BLAS of the CPU arm, whatever OMP_NUM_THREADS the launcher exported (torchrun
+    sets it to 1)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n), n
+    except Exception:
+        return None, n
+
+
 def cpu_step_rate(w, seconds=15.0, max_steps=60, warmup=1):
-    """The oracle port (NumPy fp32, OpenBLAS threads) timed on this host's cores."""
+    """The oracle port (NumPy fp32, OpenBLAS on all host threads) timed on this host's cores."""
     from oracle import rbm_oracle as O, shared_u
+    limiter, cores = host_threads()
     try:
         from threadpoolctl import threadpool_info
-        cores = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+        cores = max([i.get("num_threads", 1) for i in threadpool_info()] or [cores])
     except Exception:
-        cores = os.cpu_count() or 1
+        pass
     kind, V, H, B, k = w["kind"], w["V"], w["H"], w["B"], w["k"]
     data = synth(kind, max(w["N"] if w["N"] < 1000 else 1000, B), V, 1)
     L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(123), dtype=np.float32)
@@ -177,7 +199,7 @@ def cpu_step_rate(w, seconds=15.0, max_steps=60, warmup=1):
 def run_reference(args, w, wname):
     """--impl reference: the reference's CPU path for this step.  Theano cannot be installed here
     (SURVEY.md 8c), so this is the oracle PORT (NumPy restatement pinned to the reference source,
-    oracle/rbm_oracle.py) on all host threads; rank 0 only."""
+    oracle/rbm_oracle.py) on ALL host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -187,25 +209,93 @@ def run_reference(args, w, wname):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, "layer": "%d->%d" % (w["V"], w["H"]), "batch": w["B"], "k": w["k"],
-                   "pcd": w["pcd"]},
+        "config": config_of(wname, w),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d CD steps of the workload timed (median), NumPy/OpenBLAS fp32 oracle port; "
-                                   "Theano itself is not installable" % n},
+                         "sample": "%d CD steps of the workload timed (median), NumPy/OpenBLAS fp32 oracle port on %d "
+                                   "threads; Theano itself is not installable" % (n, cores)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def dp_extra(torch, dist, M, dev, world, rank, k, steps=12):
+    """Large-batch data-parallel CD (BASELINE.json configs[4]): RBM 784->500, B = 8192, PCD-k on the tcgen05 TF32
+    path; the minibatch rows and chains are sharded over the ranks and the packed statistics all-reduced.
+    Rank 0 first times the same step alone (the N = 1 figure of THIS run), then all ranks time the sharded one."""
+    from mdbn_b200.parallel import DataParallel
+    V, H, B = 784, 500, 8192
+    data = torch.from_numpy(synth(0, 16384, V, 1)).to(dev)
+
+    def make(rows, dp):
+        m = M.RBM(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(123), theano_rng=M.RandomStreams(1000))
+        P = M.shared(np.zeros((rows, H), np.float32))
+        cost, upd = m.get_cost_updates(lr=0.1, k=k, weightcost=0.0002, batch_size=B, persistent=P)
+        fn = m.make_train_fn(data, cost, upd, path="tensor", tf32=True)
+        fn.sync = False
+        if dp:
+            fn.dp = DataParallel()
+        return fn
+    idx = [torch.arange(i * B, (i + 1) * B, dtype=torch.int32, device=dev) for i in range(2)]
+
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for s in range(n):
+            fn(idx[s & 1], 0.9)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / n
+    ms1 = None
+    if rank == 0:
+        f1 = make(B, False)
+        timed(f1, 4)
+        ms1 = timed(f1, steps)
+        del f1
+    dist.barrier()
+    fN = make(B // world, True)
+    timed(fN, 4)
+    dist.barrier()
+    msN = timed(fN, steps)
+    t = torch.tensor([msN], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    msN = float(t.item())
+    if rank != 0:
+        return None
+    v1, vN = B / (ms1 * 1e-3), B / (msN * 1e-3)
+    return {"workload": "rbm_784x500_b8192_pcd%d_tf32" % k, "value": vN, "unit": "samples/s", "ms_per_step": msN,
+            "value_n1_same_run": v1, "efficiency_vs_n1": vN / (world * v1), "scaling": "strong",
+            "parallelism": "minibatch rows and chains sharded over %d ranks + all-reduce of the packed statistics" % world}
+
+
+def mdbn_wallclock(torch, dist, world, rank, scale):
+    """MDBN pretrain wall-clock (BASELINE.json metric, part 2): AML-shaped synthetic modalities, one DBN per
+    modality per GPU (round-robin), joint DBN on rank 0; the reference's early-stopping logic unchanged."""
+    from mdbn_b200.parallel import train_modalities, aml_synthetic_specs
+    specs = aml_synthetic_specs(scale)
+    np.random.seed(20161230 + rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    train_modalities(specs, batch_size=20, top=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=204)
+    ap.add_argument("--warmup", type=int, default=34)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the MDBN wall-clock and data-parallel legs")
+    ap.add_argument("--mdbn-scale", type=float, default=1.0)
     ap.add_argument("--replicas", type=int, default=4)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -216,7 +306,6 @@ def main():
     import torch
     import torch.distributed as dist
     import mdbn_b200 as M
-    from mdbn_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,38 +326,59 @@ def main():
     cls = M.GRBM if kind == 1 else M.RBM
     R = max(1, args.replicas) if not tensor else 1     # large-batch working sets already exceed L2
     Bl = B // world if dp else B                       # rows (and chains) this rank owns
-    fns, layers = [], []
-    for r in range(R):
+
+    def make_fn(r, dataset):
         m = cls(n_visible=V, n_hidden=H, numpy_rng=np.random.RandomState(123 + r),
                 theano_rng=M.RandomStreams(1000 + 17 * r + rank))
         P = M.shared(np.zeros((Bl, H), np.float32)) if w["pcd"] else None
         cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
                                        batch_size=B, persistent=P)
-        fn = m.make_train_fn(data, cost, upd, path=path, tf32=tensor)
+        fn = m.make_train_fn(dataset, cost, upd, path=path, tf32=tensor)
         fn.sync = False
         if dp:
             from mdbn_b200.parallel import DataParallel
             fn.dp = DataParallel()
-        fns.append(fn)
-        layers.append(m)
+        return m, fn
+    layers, fns = zip(*[make_fn(r, data) for r in range(R)])
     ctx = layers[0].ctx
     n_rows = data.shape[0]
     n_mb = n_rows // B
     rs = np.random.RandomState(5)
     perm = torch.from_numpy(rs.permutation(n_rows)[: n_mb * B].astype(np.int32)).to(dev)
     mbs = [perm[i * B:(i + 1) * B] for i in range(n_mb)]
+    # an epoch per launch, as DBN.training / RBM.learn_model issue it (src/dbn.py:444-455 is the loop they chain)
+    chained = not tensor and not dp and n_mb >= 2
+    chain = min(n_mb, 32) if chained else 1
+    idx_mat = perm[: chain * B].view(chain, B)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, rotate):
+    def issue(n_steps, rotate, per_launch):
+        """n_steps CD steps: `per_launch` minibatches per launch, the parameter sets rotate between launches."""
+        done, l = 0, 0
+        while done < n_steps:
+            n = min(per_launch, n_steps - done)
+            f = fns[l % R if rotate else 0]
+            if per_launch > 1:
+                f.run_steps(idx_mat[:n], w["mom"])
+            else:
+                f(mbs[done % n_mb], w["mom"])
+            done += n
+            l += 1
+        return l
+
+    def timed(n_steps, rotate, per_launch):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        # pre-roll: a spin kernel keeps the stream busy (~1 ms) while the host enqueues the launches behind it, so the
+        # events bracket device time of exactly n_steps steps and not the host's enqueue latency of the first launch
+        # (a training loop of thousands of launches runs with the host ahead of the device)
+        torch.cuda._sleep(2000000)
         ev0.record()
-        for s in range(n_steps):
-            fns[s % R if rotate else 0](mbs[s % n_mb], w["mom"])
+        issue(n_steps, rotate, per_launch)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -278,134 +388,157 @@ def main():
             ms = float(t.item())
         return ms
 
-    timed(args.warmup, True)                                   # warm-up (untimed)
+    timed(max(args.warmup, 2 * R * chain if chained else args.warmup), True, chain)   # warm-up (untimed): every set, twice
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.15)
     l0 = ctx.launches
-    ms = timed(args.steps, True)                               # ---- the timed region ----
+    ms = timed(args.steps, True, chain)                        # ---- the timed region ----
     launches = ctx.launches - l0
     # keep the GPU busy a little longer so that the 50 ms clock sampler sees it under load
     t_hold = time.time() + 0.6
     while time.time() < t_hold:
-        timed(50, True)
+        timed(2 * chain if chained else 50, True, chain)
     clocks = sampler.stop() if sampler else None
-    ms_warm = timed(args.steps, False)                         # same step, single parameter set (L2-warm)
-    # an epoch per launch (TrainFn.run_steps -> mdbn_cd_steps): what DBN.training actually issues.  Parameter
-    # sets still rotate between launches, but inside a launch the layer's 64 MB stay in L2 — reported next
-    # to the headline, never as the headline.
-    chained = None
-    if not tensor and not dp and n_mb >= 2:
-        chain = min(n_mb, 32)
-        idx_mat = perm[: chain * B].view(chain, B)
-        n_l = max(2, args.steps // chain)
-
-        def timed_chained():
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            ev0.record()
-            for l in range(n_l):
-                fns[l % R].run_steps(idx_mat, w["mom"])
-            ev1.record()
-            barrier()
-            return ev0.elapsed_time(ev1)
-        timed_chained()
-        ms_c = timed_chained() / (n_l * chain)
-        chained = {"steps_per_launch": chain, "ms_per_step": ms_c, "value": world * B / (ms_c * 1e-3),
-                   "note": "one launch per epoch of %d minibatches; weights L2-resident inside a launch" % chain}
     ms_per_step = ms / args.steps
     value = (1 if dp else world) * B / (ms_per_step * 1e-3)
+    # beside the headline: one launch per minibatch (cold rotation), and the chained form on ONE set (L2-warm)
+    single = warm = None
+    if chained:
+        timed(max(args.warmup, 2 * R), True, 1)
+        ms_single = timed(args.steps, True, 1) / args.steps
+        ms_warm = timed(args.steps, False, chain) / args.steps
+        single = {"ms_per_step": ms_single, "value": world * B / (ms_single * 1e-3)}
+        warm = {"ms_per_step": ms_warm, "value": world * B / (ms_warm * 1e-3)}
 
-    # ---- end to end: host minibatch -> pinned -> H2D -> step -> D2H cost, every step ----
-    n_host = 8 if not tensor else 2
-    host_mb = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, B)])).pin_memory() for _ in range(n_host)]
-    stage = torch.empty((B, V), dtype=torch.float32, device=dev)
-    e2e_fns = []
-    for r in range(R):
-        m = layers[r]
-        P = M.shared(np.zeros((Bl, H), np.float32)) if w["pcd"] else None
-        cost, upd = m.get_cost_updates(lr=w["lr"], k=k, lambda_1=w["l1"], lambda_2=w["l2"], weightcost=w["wc"],
-                                       batch_size=B, persistent=P)
-        f2 = m.make_train_fn(stage, cost, upd, path=path, tf32=tensor)   # sync=True: returns the cost as a Python float
-        if dp:
-            f2.dp = fns[0].dp
-        e2e_fns.append(f2)
-    rows = torch.arange(B, dtype=torch.int32, device=dev)
-    n_e2e = min(args.steps, 400)
+    # ---- end to end: host minibatches -> pinned -> H2D -> steps -> D2H costs, every launch ----
+    if chained:
+        n_host = 2 * R
+        host_chunks = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, chain * B)]).reshape(chain, B, V)).pin_memory()
+                       for _ in range(n_host)]
+        stage = torch.empty((chain * B, V), dtype=torch.float32, device=dev)
+        e2e_fns = [make_fn(r, stage)[1] for r in range(R)]
+        n_e2e_launches = max(2, -(-min(args.steps, 408) // chain))
+        n_e2e = n_e2e_launches * chain
 
-    def e2e_loop(n):
-        # public streaming call: every step's minibatch is copied host -> device inside the loop (double
-        # buffered on a copy stream, overlapping the previous kernel) and the step's cost is read back
-        acc = 0.0
-        nh = len(host_mb)
-        if dp or tensor:
+        def e2e_loop(nl):
+            # public streaming call: every launch's minibatches are copied host -> device inside the loop (double
+            # buffered on a copy stream, overlapping the previous launch) and the costs of every step are read back
+            acc = 0.0
+            for l in range(nl):
+                c = e2e_fns[l % R].run_steps_from_host(host_chunks[l % n_host], w["mom"],
+                                                       next_host_chunk=host_chunks[(l + R) % n_host], lag=1)
+                acc += sum(c) if c is not None else 0.0
+            for f in e2e_fns:
+                c = f.flush_chunk()
+                acc += sum(c) if c is not None else 0.0
+            return acc
+        e2e_loop(3 * R)                                   # every rotating function warmed (set-up, pinned buffers, streams)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(n_e2e_launches)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e_path = ("RBM.make_train_fn(...).run_steps_from_host -> mdbn_cd_steps (C ABI): an epoch of pinned host "
+                    "minibatches per launch, double-buffered H2D on a copy stream, every step's cost copied D2H")
+    else:
+        n_host = 2
+        host_mb = [torch.from_numpy(np.ascontiguousarray(data_h[rs.randint(0, n_rows, B)])).pin_memory() for _ in range(n_host)]
+        stage = torch.empty((B, V), dtype=torch.float32, device=dev)
+        e2e_fns = []
+        for r in range(R):
+            f2 = make_fn(r, stage)[1]
+            f2.sync = True
+            e2e_fns.append(f2)
+        rows = torch.arange(B, dtype=torch.int32, device=dev)
+        n_e2e = min(args.steps, 400)
+
+        def e2e_loop(n):
+            acc = 0.0
             for s in range(n):
-                stage.copy_(host_mb[s % nh], non_blocking=True)
+                stage.copy_(host_mb[s % n_host], non_blocking=True)
                 acc += e2e_fns[s % R](rows, w["mom"])
             return acc
-        for s in range(n):
-            # the parameter sets rotate, so each function prefetches the batch of ITS next turn; costs come
-            # back one call late (lag=1) and the last ones are flushed inside the timed region
-            c = e2e_fns[s % R].step_from_host(host_mb[s % nh], w["mom"], next_host_batch=host_mb[(s + R) % nh], lag=1)
-            acc += c if c is not None else 0.0
-        for f in e2e_fns:
-            c = f.flush()
-            acc += c if c is not None else 0.0
-        return acc
-    e2e_loop(max(3, args.warmup // 2))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(n_e2e)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+        e2e_loop(max(3, 2 * R))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(n_e2e)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e_path = "TrainFn.__call__ on a staging buffer filled from pinned host memory every step; cost read back every step"
     if world > 1:
         t = torch.tensor([t_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = (1 if dp else world) * B * n_e2e / t_e2e
 
+    # ---- the two partitions of the path that DO exchange data, reported beside the headline ----
+    extras = {}
+    if not args.no_extras and not tensor:
+        del e2e_fns
+        torch.cuda.empty_cache()
+        try:
+            extras["mdbn_aml_wallclock_s"] = mdbn_wallclock(torch, dist, world, rank, args.mdbn_scale)
+            extras["mdbn_aml"] = {"config": "AML-shaped synthetic: ME 559->40 (k=10), GE 19937->400->40, SM 1686->200->20, "
+                                            "joint 100->24->3, N=170, batch 20 (BASELINE.json configs[3])",
+                                  "scale": args.mdbn_scale,
+                                  "parallelism": "one modality DBN per GPU (round-robin over %d), joint DBN on rank 0" % world}
+        except Exception as e:      # never lose the headline line to an extra
+            extras["mdbn_aml_error"] = repr(e)[:300]
+        if world > 1:
+            try:
+                extras["dp"] = [dp_extra(torch, dist, M, dev, world, rank, kk) for kk in (1, 10)]
+            except Exception as e:
+                extras["dp_error"] = repr(e)[:300]
+
     if rank == 0:
         peak, how = peaks()
         abytes = algorithmic_bytes(w)
         achieved = abytes / (ms_per_step * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
+            tj = json.load(open(tp))
+            traffic = tj.get(args.workload)
+            traffic_note = tj.get("_how")
         if tensor:
             tpeak = tf32_peak_tflops(torch, dev)
             aflops = algorithmic_flops(w) / (world if dp else 1)
             ach = aflops / (ms_per_step * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                    "traffic": None, "kernel": "tc_gemm_kernel (tcgen05 tf32; %d GEMM launches per step)" % (2 * k + 2 + (1 if w["pcd"] else 0)),
+                    "traffic": None, "kernel": "tc_gemm_kernel (tcgen05 tf32)",
                     "peak_source": "measured here: torch.matmul 8192^3 TF32, best of 10 (MEASURED_PEAKS.json has no TF32 row)",
                     "algorithmic_flops_per_step_per_gpu": aflops}
         else:
-            roof = None
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_how": traffic_note, "kernel": "cd_skinny_kernel", "peak_source": how,
+                    "algorithmic_bytes_per_step": abytes, "steps_per_launch": chain,
+                    "algorithmic_bytes_per_launch": abytes * chain}
+            if single:
+                roof["single_launch"] = {"ms_per_step": single["ms_per_step"], "value": single["value"],
+                                         "frac": abytes / (single["ms_per_step"] * 1e-3) / 1e9 / peak}
+                roof["l2_warm"] = {"ms_per_step": warm["ms_per_step"], "value": warm["value"],
+                                   "frac": abytes / (warm["ms_per_step"] * 1e-3) / 1e9 / peak}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if dp else "weak",
             "vs_baseline": None, "dtype": "tf32" if tensor else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "layer": "%s %d->%d" % ("GRBM" if kind else "RBM", V, H),
-                       "batch": B, "k": k, "pcd": w["pcd"], "rng": "philox4x32-10 in-kernel",
-                       "l2": ("inputs larger than L2: activations + dataset of a %d-row batch" % B) if tensor else
-                             ("steps rotate over %d independent parameter sets (%.0f MB > L2) so weights stream from HBM"
-                              % (R, R * 2 * V * H * 4 / 1e6)),
-                       "parallelism": ("minibatch rows sharded over %d ranks + NCCL all-reduce of the packed statistics" % world)
-                       if dp else "one independent layer per GPU (modality-parallel), no collective"},
+            "config": config_of(args.workload, w),
+            "notes": {"rng": "philox4x32-10 in-kernel",
+                      "launches": ("one launch per epoch of %d minibatches (TrainFn.run_steps -> mdbn_cd_steps), as "
+                                   "DBN.training issues them" % chain) if chained else "one launch sequence per step",
+                      "l2": ("inputs larger than L2: activations + dataset of a %d-row batch" % B) if tensor else
+                            ("the parameter sets rotate over %d independent layers between launches (%.0f MB > L2): every "
+                             "launch starts with its weights in HBM" % (R, R * 2 * V * H * 4 / 1e6)),
+                      "parallelism": ("minibatch rows sharded over %d ranks + NCCL all-reduce of the packed statistics" % world)
+                      if dp else "one independent layer per GPU (modality-parallel), no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": 4,
-                    "steps": n_e2e, "path": "RBM.make_train_fn(...).step_from_host -> mdbn_cd_step (C ABI): pinned host minibatch, double-buffered H2D on a copy stream, every step's cost copied D2H (returned one call late)"},
+                    "steps": n_e2e, "path": e2e_path},
             "gpu_launches": int(launches),
-            "roofline": roof if roof else
-            {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-             "traffic": traffic, "kernel": "cd_skinny_kernel", "peak_source": how,
-             "algorithmic_bytes_per_launch": abytes,
-             "achieved_l2_warm": abytes / (ms_warm / args.steps * 1e-3) / 1e9},
-            "value_l2_warm": world * B / (ms_warm / args.steps * 1e-3),
+            "roofline": roof,
         }
-        if chained is not None:
-            line["epoch_per_launch"] = chained
+        line.update(extras)
         if not args.no_cpu_baseline:
             v, cores, n, med = cpu_step_rate(w)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",

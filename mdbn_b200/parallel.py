@@ -118,3 +118,27 @@ def train_modalities(specs, rank=None, world=None, group=None, rng_seed=123, bat
     if top and rank == 0:
         top_dbn = MDBN.train_top(batch_size, False, joint.astype(numpy.float32), None, rng, device=device, verbose=verbose)
     return dbns, joint, top_dbn
+
+
+def aml_synthetic_specs(scale=1.0, n=170):
+    """AML-shaped synthetic MDBN workload (BASELINE.json configs[3]): shapes from the run
+    recorded in the reference's notebooks (ME 559->40, GE 19937->400->40, SM 1686->200->20, N = 170), hyper-parameters
+    from src/AMLsm.py:38-62,207-339 and src/AMLsm2.py:308-339.  `scale` shrinks every patience budget (quick checks;
+    a scaled run is NOT the named configuration)."""
+    def zs(x):
+        return ((x - x.mean(0)) / x.std(0)).astype(numpy.float32)
+    me = zs(numpy.random.RandomState(2).randn(n, 559))
+    ge = zs(numpy.random.RandomState(3).randn(n, 19937))
+    rs = numpy.random.RandomState(4)
+    sm_raw = (rs.rand(n, 1686) < 0.007) * rs.choice([1, 2, 3], size=(n, 1686), p=[0.985, 0.0146, 0.0004])
+    sm_raw[0] += (sm_raw.sum(0) == 0)          # no zero-variance columns (the reference drops them, src/utils.py:97)
+    sm = zs(sm_raw.astype(numpy.float64))
+    sc = lambda xs: [max(2, int(round(x * scale))) for x in xs]
+    return {
+        "ME": dict(data=me, layers_sizes=[40], pretraining_epochs=sc([80000]), pretrain_lr=[0.005], k=10,
+                   lambda_1=0.01, lambda_2=0.01),
+        "GE": dict(data=ge, layers_sizes=[400, 40], pretraining_epochs=sc([8000, 800]), pretrain_lr=[0.005, 0.1], k=1,
+                   lambda_1=0.01, lambda_2=0.1),
+        "SM": dict(data=sm, layers_sizes=[200, 20], pretraining_epochs=sc([8000, 800]), pretrain_lr=[0.005, 0.1], k=1,
+                   lambda_1=0.01, lambda_2=0.01),
+    }

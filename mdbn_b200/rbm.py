@@ -185,6 +185,83 @@ class TrainFn:
         lg["ev"][k].synchronize()
         return float(lg["host"][k][0])
 
+    def run_steps_from_host(self, host_chunk, momentum=0.0, lr=None, next_host_chunk=None, lag=0):
+        """`n` consecutive steps on minibatches that live in (pinned) HOST memory: host_chunk is [n, B, V] float32 —
+        the streaming form of run_steps (an epoch, or the minibatches up to the next validation point) for datasets
+        kept off the device.  The chunk is copied into one of two device staging buffers on a copy stream (the copy
+        of `next_host_chunk` is enqueued right behind this chunk's launch and overlaps it), the n steps run as ONE
+        mdbn_cd_steps launch on it, and the n costs are copied back on a third stream.
+        lag=0: returns the n costs of THIS chunk (list of floats).  lag=1: returns those of the PREVIOUS call (None on
+        the first; `flush_chunk()` returns the last) so that the host never blocks between launches."""
+        n, B, V = (int(x) for x in host_chunk.shape)
+        st = getattr(self, "_feedc", None)
+        if st is None or st["shape"] != (n, B, V):
+            main = torch.cuda.current_stream()
+            copy, d2h = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+            st = self._feedc = {
+                "shape": (n, B, V), "cur": 0, "staged": [None, None], "nbytes": n * B * V * 4,
+                "buf": [torch.empty((n * B, V), dtype=torch.float32, device=self.device) for _ in range(2)],
+                "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()],
+                "copy": copy, "copy_h": ctypes.c_void_p(copy.cuda_stream), "main": main,
+                "main_h": ctypes.c_void_p(main.cuda_stream), "d2h": d2h, "d2h_h": ctypes.c_void_p(d2h.cuda_stream),
+                "rows": torch.arange(n * B, dtype=torch.int32, device=self.device).view(n, B),
+                "cost_dev": [torch.zeros(n, dtype=torch.float32, device=self.device) for _ in range(2)],
+                "cost_host": [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(2)],
+                "ev": [torch.cuda.Event(), torch.cuda.Event()], "n": 0, "pending": None}
+        lib = self.rbm.ctx.lib
+        main, copy = st["main"], st["copy"]
+
+        def stage(slot, chunk):
+            if chunk.dtype != torch.float32 or not chunk.is_contiguous():
+                raise TypeError("run_steps_from_host takes contiguous float32 [n, B, V] host tensors (pinned for overlap)")
+            if st["staged"][slot] is not None:
+                copy.wait_event(st["free"][slot])
+            _lib.check(lib.mdbn_copy_async(st["buf"][slot].data_ptr(), chunk.data_ptr(), st["nbytes"], st["copy_h"]))
+            st["ready"][slot].record(copy)
+            st["staged"][slot] = chunk
+        cur = st["cur"]
+        if st["staged"][cur] is not host_chunk:                  # not prefetched by the previous call
+            stage(cur, host_chunk)
+        main.wait_event(st["ready"][cur])
+        k = st["n"] & 1
+        if st["n"] >= 2:
+            main.wait_event(st["ev"][k])                         # cost slot k was read back two calls ago
+        sync, self.sync = self.sync, False
+        try:
+            self._call(st["rows"], momentum, lr, data_override=st["buf"][cur], stream=st["main_h"],
+                       n_steps=n, costs=st["cost_dev"][k])
+        finally:
+            self.sync = sync
+        st["free"][cur].record(main)
+        nxt = 1 - cur
+        if next_host_chunk is not None:
+            stage(nxt, next_host_chunk)
+        else:
+            st["staged"][nxt] = None
+        st["cur"] = nxt
+        st["d2h"].wait_event(st["free"][cur])
+        _lib.check(lib.mdbn_copy_async(st["cost_host"][k].data_ptr(), st["cost_dev"][k].data_ptr(), 4 * n, st["d2h_h"]))
+        st["ev"][k].record(st["d2h"])
+        prev, st["n"] = st["pending"], st["n"] + 1
+        if not lag:
+            st["pending"] = None
+            st["ev"][k].synchronize()
+            return [float(c) for c in st["cost_host"][k]]
+        st["pending"] = k
+        if prev is None:
+            return None
+        st["ev"][prev].synchronize()
+        return [float(c) for c in st["cost_host"][prev]]
+
+    def flush_chunk(self):
+        """Costs of the last lagged chunk (run_steps_from_host(..., lag=1)); None when nothing is pending."""
+        st = getattr(self, "_feedc", None)
+        if not st or st["pending"] is None:
+            return None
+        k, st["pending"] = st["pending"], None
+        st["ev"][k].synchronize()
+        return [float(c) for c in st["cost_host"][k]]
+
     def run_steps(self, index_matrix, momentum=0.0, lr=None):
         """`n` consecutive steps from an [n, B] matrix of row numbers — an epoch, or the minibatches up to the
         next validation point (src/dbn.py:343-353).  Same parameters, chains and costs as n single calls;

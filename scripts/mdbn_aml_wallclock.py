@@ -24,21 +24,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 from mdbn_b200.parallel import train_modalities
 
-def zs(x):
-    return ((x - x.mean(0)) / x.std(0)).astype(np.float32)
-N = 170
-me = zs(np.random.RandomState(2).randn(N, 559))
-ge = zs(np.random.RandomState(3).randn(N, 19937))
-rs = np.random.RandomState(4)
-sm_raw = (rs.rand(N, 1686) < 0.007) * rs.choice([1, 2, 3], size=(N, 1686), p=[0.985, 0.0146, 0.0004])
-sm_raw[0] += (sm_raw.sum(0) == 0)          # no zero-variance columns (the reference drops them, src/utils.py:97)
-sm = zs(sm_raw.astype(np.float64))
-sc = lambda xs: [max(2, int(round(x * args.scale))) for x in xs]
-specs = {
-    "ME": dict(data=me, layers_sizes=[40], pretraining_epochs=sc([80000]), pretrain_lr=[0.005], k=10, lambda_1=0.01, lambda_2=0.01),
-    "GE": dict(data=ge, layers_sizes=[400, 40], pretraining_epochs=sc([8000, 800]), pretrain_lr=[0.005, 0.1], k=1, lambda_1=0.01, lambda_2=0.1),
-    "SM": dict(data=sm, layers_sizes=[200, 20], pretraining_epochs=sc([8000, 800]), pretrain_lr=[0.005, 0.1], k=1, lambda_1=0.01, lambda_2=0.01),
-}
+from mdbn_b200.parallel import aml_synthetic_specs
+specs = aml_synthetic_specs(args.scale)
 np.random.seed(20161230 + rank)
 torch.cuda.synchronize()
 if world > 1:
