@@ -329,6 +329,43 @@ def get_minibatches_idx(n, batch_size, shuffle=False, rng=None):
 
 
 # ---------------------------------------------------------------------------
+# standalone epoch loop                  src/rbm.py:484-629 (RBM.training / learn_model), :701-728 (GRBM.training)
+# ---------------------------------------------------------------------------
+def rbm_training(L, train, val, training_epochs, batch_size=10, learning_rate=None, k=1, initial_momentum=0.0,
+                 final_momentum=0.0, weightcost=0.0, lambda_1=0.0, lambda_2=None, persistent=None, u_provider=None):
+    """RBM.training (:484-520): PCD with a chain of zeros by default (`persistent=True`), `lambda_2` accepted and NOT
+    forwarded (:504-509).  GRBM.training (:701-728): always CD (`persistent` accepted and not forwarded, :711-717),
+    lambda_1 / lambda_2 forwarded, defaults lr 0.01 / lambda_2 0.1.  Then learn_model (:522-629): momentum switches
+    to `final_momentum` at 0-based epoch 6 (:584), shuffled minibatches from the GLOBAL numpy RNG (:587-589),
+    per epoch the mean cost and the free-energy gap of train[0:n_val] vs val (:597-600).
+    u_provider(call_index, B) -> the shared random buffer of that step.  Returns [(mean cost, gap)] per epoch."""
+    if L.kind == GRBM:
+        lr = 0.01 if learning_rate is None else learning_rate
+        l1, l2 = lambda_1, (0.1 if lambda_2 is None else lambda_2)
+        chain = None
+    else:
+        lr = 0.1 if learning_rate is None else learning_rate
+        l1, l2 = 0.0, 0.0
+        use_pcd = True if persistent is None else bool(persistent)
+        chain = np.zeros((batch_size, L.n_hidden), dtype=L.W.dtype) if use_pcd else None
+    W_snap = L.W.copy()                                        # :414-415, captured by get_cost_updates
+    n, n_val = train.shape[0], val.shape[0]
+    momentum, history, call = initial_momentum, [], 0
+    for epoch in range(training_epochs):
+        if epoch == 6:                                         # :584
+            momentum = final_momentum
+        _, minibatches = get_minibatches_idx(n, batch_size, shuffle=True)
+        costs = []
+        for mb in minibatches:
+            U = u_provider(call, len(mb))
+            costs.append(cd_step(L, train[mb], U, lr=lr, k=k, lambda_1=l1, lambda_2=l2, weightcost=weightcost,
+                                 batch_size=batch_size, momentum=momentum, persistent=chain, W_snap=W_snap))
+            call += 1
+        history.append((float(np.mean(costs)), float(free_energy_gap(L, train[:n_val], val))))
+    return history
+
+
+# ---------------------------------------------------------------------------
 # DBN stack + greedy loop                src/dbn.py:64-204, 238-332, 334-517
 # ---------------------------------------------------------------------------
 class DBN:

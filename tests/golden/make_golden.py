@@ -305,6 +305,54 @@ def mdbn_case(name, seed=5):
 
 
 
+# ---------------------------------------------------------------------------
+# F. RBM.training / GRBM.training / learn_model   src/rbm.py:484-629, 701-728
+# ---------------------------------------------------------------------------
+def training_case(name, kind, V, H, N, n_val, B, epochs, seed, shuffle_seed, **kw):
+    """The standalone epoch loop: PCD by default for the RBM (chain of zeros, :490-498), always CD for the GRBM
+    (`persistent` is accepted and not forwarded, :711-717), momentum switch at 0-based epoch 6 (:584), per-epoch
+    mean cost and free-energy gap on train[0:n_val] vs the validation set (:597-600)."""
+    x, m = build(kind, V, H, seed)
+    rs = np.random.RandomState(seed + 5)
+    train, val = make_data(rs, N, V, kind), make_data(rs, n_val, V, kind)
+    W0 = m.W.get_value()
+    base = m.theano_rng.n_nodes
+    k = kw.get("k", 1)
+    orig_function = theano.function
+
+    def hooked(*a, **k2):
+        f = orig_function(*a, **k2)
+        if k2.get("name") == "train_rbm":
+            PROV.register(f, base, 0, kind, True, V, H, k)
+        return f
+    theano.function = hooked
+    ref_rbm.theano.function = hooked
+    np.random.seed(shuffle_seed)
+    buf = io.StringIO()
+    try:
+        with redirect_stdout(buf), redirect_stderr(io.StringIO()):
+            m.training(theano.shared(train, borrow=True), theano.shared(val, borrow=True), epochs, batch_size=B, **kw)
+    finally:
+        theano.function = orig_function
+        ref_rbm.theano.function = orig_function
+    costs, fegs = [], []
+    for line in buf.getvalue().splitlines():
+        if line.startswith("Training epoch"):
+            costs.append(float(line.split("cost is")[1]))
+        if line.startswith("Free energy gap is"):
+            fegs.append(float(line.split("is")[1]))
+    assert len(costs) == epochs and len(fegs) == epochs, (len(costs), len(fegs))
+    out = dict(kind=kind, V=V, H=H, N=N, n_val=n_val, B=B, epochs=epochs, seed=seed, shuffle_seed=shuffle_seed,
+               seed_u=SEED_U, k=k, train=train, val=val, W0=W0, costs=np.array(costs), fegs=np.array(fegs),
+               W=m.W.get_value(), hbias=m.hbias.get_value(), vbias=m.vbias.get_value(),
+               W_speed=m.W_speed.get_value(), hbias_speed=m.hbias_speed.get_value(),
+               vbias_speed=m.vbias_speed.get_value())
+    for key, v in kw.items():
+        out["kw_" + key] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "costs", np.round(costs, 4), "feg", np.round(fegs, 4))
+
+
 def io_case():
     """the table loader / pre-processing before the path, the class extraction after it and the
     .npz checkpoint written by the experiment scripts — all produced by the reference's own functions."""
@@ -407,6 +455,14 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["io"]:          # only the 8f rows (the other files are unchanged by it)
         io_case()
         sys.exit(0)
+    if sys.argv[1:] == ["training"]:    # only the standalone epoch loops
+        training_case("train_rbm_pcd", O.RBM, 24, 10, 45, 6, 5, 8, seed=61, shuffle_seed=881, learning_rate=0.1, k=1,
+                      initial_momentum=0.5, final_momentum=0.9, weightcost=0.0002)
+        training_case("train_rbm_cd2", O.RBM, 24, 10, 43, 6, 5, 7, seed=62, shuffle_seed=882, learning_rate=0.05, k=2,
+                      initial_momentum=0.5, final_momentum=0.9, weightcost=0.0002, persistent=False)
+        training_case("train_grbm", O.GRBM, 24, 10, 45, 6, 5, 8, seed=63, shuffle_seed=883, learning_rate=0.01, k=1,
+                      initial_momentum=0.0, final_momentum=0.5, lambda_1=0.01, lambda_2=0.1, persistent=True)
+        sys.exit(0)
     phases_case("phases_rbm", O.RBM, 13, 7, 5, seed=11)
     phases_case("phases_grbm", O.GRBM, 13, 7, 5, seed=12)
     phases_case("phases_grbm_noisy", O.GRBM, 13, 7, 5, seed=13, ef=False)
@@ -440,4 +496,10 @@ if __name__ == "__main__":
              lrs=[0.1, 0.1, 0.1], lambda_1=0.0, lambda_2=0.1, gauss=False, seed=52, shuffle_seed=778)
     minibatch_case()
     mdbn_case("mdbn_small")
+    training_case("train_rbm_pcd", O.RBM, 24, 10, 45, 6, 5, 8, seed=61, shuffle_seed=881, learning_rate=0.1, k=1,
+                  initial_momentum=0.5, final_momentum=0.9, weightcost=0.0002)
+    training_case("train_rbm_cd2", O.RBM, 24, 10, 43, 6, 5, 7, seed=62, shuffle_seed=882, learning_rate=0.05, k=2,
+                  initial_momentum=0.5, final_momentum=0.9, weightcost=0.0002, persistent=False)
+    training_case("train_grbm", O.GRBM, 24, 10, 45, 6, 5, 8, seed=63, shuffle_seed=883, learning_rate=0.01, k=1,
+                  initial_momentum=0.0, final_momentum=0.5, lambda_1=0.01, lambda_2=0.1, persistent=True)
     io_case()

@@ -294,6 +294,34 @@ def test_mdbn_vs_golden():
 # ---------------------------------------------------------------------------
 # production RNG (Philox4x32-10 in-kernel)
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["train_rbm_pcd", "train_rbm_cd2", "train_grbm"])
+def test_standalone_training_vs_golden(name):
+    """RBM.training / GRBM.training / learn_model against the reference's own run (src/rbm.py:484-629, 701-728):
+    PCD by default with a chain of zeros, momentum switch at 0-based epoch 6, per-epoch mean cost and free-energy
+    gap; `persistent` is ignored by the GRBM exactly like the reference."""
+    g = load(name)
+    m = M()
+    kind, V, H, B, k = int(g["kind"]), int(g["V"]), int(g["H"]), int(g["B"]), int(g["k"])
+    prov = lambda layer, call, b: shared_u.step_buffer(int(g["seed_u"]), 0, call, kind, True, b, V, H, k)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    r = cls(n_visible=V, n_hidden=H, W=g["W0"].astype(np.float32), theano_rng=m.BufferStreams(prov))
+    kw = {key[3:]: g[key].item() for key in g if key.startswith("kw_")}
+    np.random.seed(int(g["shuffle_seed"]))
+    import io
+    from contextlib import redirect_stdout
+    with redirect_stdout(io.StringIO()):
+        hist = r.training(g["train"].astype(np.float32), g["val"].astype(np.float32), int(g["epochs"]), batch_size=B, **kw)
+    costs, fegs = np.array([h[0] for h in hist]), np.array([h[1] for h in hist])
+    # fp32 run vs the reference's float64 run on fp32-rounded inputs: the 1 % bar of the north star, and much tighter
+    # while no Bernoulli sample has flipped
+    assert np.all(np.abs(costs - g["costs"]) <= 1e-2 * np.abs(g["costs"])), (costs, g["costs"])
+    assert np.all(np.abs(fegs - g["fegs"]) <= 1e-2 * np.abs(g["fegs"]) + 1e-3), (fegs, g["fegs"])
+    np.testing.assert_allclose(costs, g["costs"], rtol=2e-4)
+    close(r.W.get_value(), g["W"], rtol=5e-5, what="W after %d epochs" % int(g["epochs"]))
+    close(r.hbias.get_value(), g["hbias"], rtol=5e-5, scale=max(np.abs(g["hbias"]).max(), 1e-3), what="hbias")
+    close(r.vbias.get_value(), g["vbias"], rtol=5e-5, scale=max(np.abs(g["vbias"]).max(), 1e-3), what="vbias")
+
+
 def test_philox_sampling_statistics_and_determinism():
     m = M()
     V, H, B = 64, 4096, 64

@@ -135,6 +135,28 @@ def test_dbn_training_loop(name):
     np.testing.assert_allclose(d.get_output(g["train"]), g["out_train"], **TOL)
 
 
+@pytest.mark.parametrize("name", ["train_rbm_pcd", "train_rbm_cd2", "train_grbm"])
+def test_standalone_training_loop(name):
+    """RBM.training / GRBM.training / learn_model (src/rbm.py:484-629, 701-728) as run by the reference itself:
+    PCD default with a chain of zeros, momentum switch at 0-based epoch 6, per-epoch mean cost and free-energy gap."""
+    g = load(name)
+    kind, V, H, B, k = int(g["kind"]), int(g["V"]), int(g["H"]), int(g["B"]), int(g["k"])
+    rng = np.random.RandomState(int(g["seed"]))
+    rng.randint(2 ** 30)                                        # the Theano stream seed is drawn first (src/rbm.py:92)
+    L = O.Layer(V, H, kind, numpy_rng=rng)
+    np.testing.assert_array_equal(L.W, g["W0"])
+    kw = {key[3:]: g[key].item() for key in g if key.startswith("kw_")}
+    kw.pop("k", None)
+    np.random.seed(int(g["shuffle_seed"]))
+    hist = O.rbm_training(L, g["train"], g["val"], int(g["epochs"]), batch_size=B, k=k,
+                          u_provider=lambda call, b: shared_u.step_buffer(int(g["seed_u"]), 0, call, kind, True, b, V, H, k),
+                          **kw)
+    np.testing.assert_allclose([h[0] for h in hist], g["costs"], rtol=1e-9)
+    np.testing.assert_allclose([h[1] for h in hist], g["fegs"], rtol=1e-9)
+    for name_ in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        np.testing.assert_allclose(getattr(L, name_), g[name_], **TOL)
+
+
 def test_free_energy_bruteforce():
     """F(v) == -log sum_h exp(-E(v,h)) for a tiny Bernoulli RBM."""
     rs = np.random.RandomState(0)
