@@ -20,9 +20,10 @@
 extern "C" {
 #endif
 
-#define MDBN_ABI_VERSION 1
+#define MDBN_ABI_VERSION 2
 
 typedef struct mdbn_ctx mdbn_ctx;
+typedef struct mdbn_comm mdbn_comm;   /* NCCL communicator of the data-parallel step (below) */
 
 enum { MDBN_RBM = 0, MDBN_GRBM = 1 };                       /* src/rbm.py:46 / :631 */
 enum { MDBN_RNG_NONE = 0, MDBN_RNG_BUFFER = 1, MDBN_RNG_PHILOX = 2 };
@@ -110,7 +111,12 @@ typedef struct {
   int phase;             /* MDBN_PHASE_FULL, or STATS (fill stats_buf, no update) / APPLY (update from stats_buf) */
   float* stats_buf;      /* data-parallel packing: [sum v0^T ph - nv^T nh (V*H) | sum(ph-nh) (H) | sum(v0-nv) (V) |
                             cost numerator (1) | rows (1)], raw sums over this rank's rows */
-  int B_total;           /* APPLY: rows summed over all ranks (bias means, cost mean) */
+  int B_total;           /* APPLY, or FULL with comm: rows of the whole minibatch over all ranks (bias means, cost mean) */
+  mdbn_comm* comm;       /* FULL only; non-NULL: data-parallel step.  B / indices / persistent are THIS rank's rows and chains,
+                            B_nom the batch_size argument, B_total the rows of the whole minibatch: the library runs the
+                            statistics on the shard, all-reduces the packed buffer over NCCL (two chunks on a side stream,
+                            the V*H block overlapping the tail kernels) and applies the identical update on every rank.
+                            No counterpart in the reference (single device); the sums it shards are src/rbm.py:411-417. */
 } mdbn_cd_args;
 
 /* Staging helper of the host-streaming train step (TrainFn.step_from_host): cudaMemcpyAsync(cudaMemcpyDefault)
@@ -127,6 +133,16 @@ int mdbn_cd_steps(mdbn_ctx* ctx, const mdbn_cd_args* args, int n_steps, void* st
 
 /* size in floats of stats_buf for a layer */
 long long mdbn_stats_size(int V, int H);
+
+/* Data parallelism inside the library (nothing to replace in the reference, which is single device).
+ * Rank 0 creates an id (ncclUniqueId, MDBN_COMM_ID_BYTES bytes) and hands it to the other ranks by whatever
+ * channel the host has; every rank then calls mdbn_comm_init with its device.  NCCL is loaded at run time. */
+#define MDBN_COMM_ID_BYTES 128
+int mdbn_comm_unique_id(unsigned char* id_out);
+int mdbn_comm_init(mdbn_comm** out, const unsigned char* id, int rank, int world, int device);
+int mdbn_comm_destroy(mdbn_comm* comm);
+/* in-place sum over the ranks, enqueued on `stream` (used for the small exchange of modality activations) */
+int mdbn_comm_all_reduce(mdbn_comm* comm, float* buf, unsigned long long count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,13 +36,15 @@ class CdArgs(C.Structure):
         ("lr", C.c_float), ("momentum", C.c_float), ("lambda_1", C.c_float), ("lambda_2", C.c_float),
         ("weightcost", C.c_float), ("rng", Rng), ("cost_out", C.c_void_p),
         ("path", C.c_int), ("tf32", C.c_int), ("phase", C.c_int), ("stats_buf", C.c_void_p),
-        ("B_total", C.c_int),
+        ("B_total", C.c_int), ("comm", C.c_void_p),
     ]
 
 
 EXPORTS = ("mdbn_abi_version", "mdbn_last_error", "mdbn_create", "mdbn_destroy", "mdbn_launch_count",
            "mdbn_set_tf32_phases",
-           "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_copy_async", "mdbn_stats_size")
+           "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_copy_async", "mdbn_stats_size",
+           "mdbn_comm_unique_id", "mdbn_comm_init", "mdbn_comm_destroy", "mdbn_comm_all_reduce")
+COMM_ID_BYTES = 128
 
 _lib = None
 _lock = threading.Lock()
@@ -76,9 +78,13 @@ def load():
         lib.mdbn_cd_step.argtypes = [vp, C.POINTER(CdArgs), vp]
         lib.mdbn_cd_steps.argtypes = [vp, C.POINTER(CdArgs), C.c_int, vp]
         lib.mdbn_copy_async.argtypes = [vp, vp, C.c_ulonglong, vp]
+        lib.mdbn_comm_unique_id.argtypes = [C.c_char_p]
+        lib.mdbn_comm_init.argtypes = [C.POINTER(vp), C.c_char_p, i, i, i]
+        lib.mdbn_comm_destroy.argtypes = [vp]
+        lib.mdbn_comm_all_reduce.argtypes = [vp, vp, C.c_ulonglong, vp]
         for n in EXPORTS:
             getattr(lib, n)
-        if lib.mdbn_abi_version() != 1:
+        if lib.mdbn_abi_version() != 2:
             raise MdbnError("ABI version mismatch")
         _lib = lib
     return _lib
@@ -112,6 +118,37 @@ class Context:
             if getattr(self, "handle", None):
                 self.lib.mdbn_destroy(self.handle)
                 self.handle = None
+        except Exception:
+            pass
+
+
+class Comm:
+    """NCCL communicator owned by the library (mdbn_comm): the data-parallel CD step runs entirely behind the C ABI.
+    `exchange_id(id_bytes_or_None) -> id_bytes` carries rank 0's unique id to the other ranks (the host's channel:
+    torch.distributed, MPI, a file ...)."""
+
+    def __init__(self, rank, world, device, exchange_id):
+        self.lib = load()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        if self.rank == 0:
+            check(self.lib.mdbn_comm_unique_id(buf))
+        uid = exchange_id(bytes(buf.raw) if self.rank == 0 else None)
+        h = C.c_void_p()
+        check(self.lib.mdbn_comm_init(C.byref(h), uid, self.rank, self.world, self.device))
+        self.handle = h
+
+    def all_reduce(self, tensor, stream):
+        check(self.lib.mdbn_comm_all_reduce(self.handle, tensor.data_ptr(), tensor.numel(), stream))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mdbn_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

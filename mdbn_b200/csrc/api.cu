@@ -158,6 +158,10 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   if (a->phase == MDBN_PHASE_APPLY) MDBN_CHECK(a->B_total > 0, "cd_step: APPLY needs B_total");
   MDBN_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->comm) {
+    MDBN_CHECK(a->phase == MDBN_PHASE_FULL, "cd_step: comm goes with full steps only");
+    return comm_cd_step(c, *a, st);
+  }
   int path = a->path;
   if (path == MDBN_PATH_AUTO) {
     if (a->phase == MDBN_PHASE_FULL && tiny_supported(c, *a)) path = MDBN_PATH_TINY;

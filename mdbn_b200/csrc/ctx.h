@@ -18,6 +18,9 @@ struct mdbn_ctx {
   int tf32_phases = 0;               // single-phase calls use the tcgen05 TF32 path (mdbn_set_tf32_phases)
   unsigned skinny_parity = 0;        // which of the two accumulator sets the next skinny launch uses
   unsigned long long skinny_key = 0; // layout of the accumulator scratch (re-zeroed when it changes)
+  // data-parallel step: event the statistics path records once the V*H block of the packed buffer is complete
+  cudaEvent_t ev_stats_w = nullptr;
+  bool ev_stats_w_done = false;
 };
 
 namespace mdbn {
@@ -93,6 +96,9 @@ int tensor_propup(mdbn_ctx*, const float* W, int ldw, const float* hb, const flo
 int tensor_propdown(mdbn_ctx*, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
                     int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
 int apply_update(mdbn_ctx* c, const mdbn_cd_args& a, const float* G, int rows, cudaStream_t st);
+
+// ---- data-parallel step over NCCL: comm.cu ----
+int comm_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st);
 
 // layout of the App. A random buffer
 struct ULayout {

@@ -399,6 +399,7 @@ int generic_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   }
   // statistics (:411-417): G = [v0;nv]^T (+/-) [ph;nh]
   MDBN_TRY((launch_sgemm<true, false>(c, XV, V, YH, H, G, V, H, 2 * B, 1, B, st)));
+  if (c->ev_stats_w) { MDBN_CUDA(cudaEventRecord(c->ev_stats_w, st)); c->ev_stats_w_done = true; }
   col_diff_sum_kernel<<<(H + 255) / 256, 256, 0, st>>>(YH, B, H, G + VH);
   c->launches++;
   col_diff_sum_kernel<<<(V + 255) / 256, 256, 0, st>>>(XV, B, V, G + VH + H);

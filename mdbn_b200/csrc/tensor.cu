@@ -543,6 +543,7 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
                                                 ep, st)));
     reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, VH, G);
     c->launches++;
+    if (c->ev_stats_w) { MDBN_CUDA(cudaEventRecord(c->ev_stats_w, st)); c->ev_stats_w_done = true; }
   }
   MDBN_TRY(col_diff_sum(c, YH, ldy, B, H, G + VH, st));
   MDBN_TRY(col_diff_sum(c, XV, ldx, B, V, G + VH + H, st));

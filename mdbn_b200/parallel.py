@@ -29,14 +29,31 @@ def stats_size(V, H):
 
 
 class DataParallel:
-    """All-reduce of the packed statistics.  `stats_fn(rows) -> buffer` fills this rank's packed
-    buffer for its rows, `apply_fn(buffer, rows_total)` applies the update from the reduced one;
-    on GPUs both are mdbn_cd_step phases (STATS / APPLY), in the CPU tests they are injected."""
+    """Data-parallel CD step.  Two forms:
 
-    def __init__(self, group=None):
+    * inside the library (default on GPUs): an NCCL communicator owned by libmdbn_b200.so (mdbn_comm_init); TrainFn
+      passes it in mdbn_cd_args.comm and ONE mdbn_cd_step does shard statistics -> chunked all-reduce -> update;
+    * host-level (`c_abi=False`, and the CPU tests): `stats_fn(rows) -> buffer` fills this rank's packed buffer,
+      torch.distributed all-reduces it, `apply_fn(buffer, rows_total)` applies the update."""
+
+    def __init__(self, group=None, c_abi=None, device=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.comm = None
+        if c_abi is None:
+            c_abi = torch.cuda.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+        if c_abi:
+            from . import _lib
+            dev = torch.cuda.current_device() if device is None else int(device)
+
+            def exchange(uid):
+                if self.world == 1:
+                    return uid
+                box = [uid]
+                dist.broadcast_object_list(box, src=0, group=group)
+                return box[0]
+            self.comm = _lib.Comm(self.rank, self.world, dev, exchange)
 
     def all_reduce(self, buf):
         if self.world > 1:

@@ -82,6 +82,11 @@ class TrainFn:
         return self._data
 
     def __call__(self, indexes=None, momentum=0.0, lr=None, rows=None):
+        if self.dp is not None and getattr(self.dp, "comm", None) is not None:
+            # data-parallel step inside the library: this rank's rows + the communicator, one mdbn_cd_step
+            from .parallel import shard_rows
+            mine = shard_rows(indexes, self.dp.rank, self.dp.world)
+            return self._call(mine, momentum, lr, rows_total=len(indexes), comm=self.dp.comm)
         if self.dp is not None and self.dp.world > 1:
             return self._call_dp(indexes, momentum, lr)
         return self._call(indexes, momentum, lr)
@@ -274,7 +279,7 @@ class TrainFn:
         idx = idx.reshape(1, -1) if idx.dim() == 1 else idx.contiguous()
         n = int(idx.shape[0])
         chained = (n > 1 and getattr(self.rbm.theano_rng, "mode", None) == _lib.RNG_PHILOX
-                   and not (self.dp is not None and self.dp.world > 1))
+                   and self.dp is None)
         if chained:
             costs = torch.empty(n, dtype=torch.float32, device=self.device)
             self._call(idx, momentum, lr, n_steps=n, costs=costs)
@@ -289,7 +294,7 @@ class TrainFn:
         return [float(c) for c in costs.cpu()]
 
     def _call(self, indexes, momentum=0.0, lr=None, phase=_lib.PHASE_FULL, rows_total=0, data_override=None,
-              n_steps=1, costs=None, stream=None):
+              n_steps=1, costs=None, stream=None, comm=None):
         r, h = self.rbm, self.updates.hyper
         data = self.data() if data_override is None else data_override
         if indexes is None:                      # APPLY phase: no rows of its own
@@ -309,7 +314,7 @@ class TrainFn:
             rng, keep = _lib.Rng(_lib.RNG_PHILOX, None, 0, 0), None
         else:
             rng, keep = r.theano_rng.next_rng(id(self), self.device, layer_id=self.layer_id, B=B, n_steps=n_steps)
-            if self.dp is not None and self.dp.world > 1 and rng.mode == _lib.RNG_PHILOX:
+            if self.dp is not None and self.dp.world > 1 and rng.mode == _lib.RNG_PHILOX and phase != _lib.PHASE_APPLY:
                 # data-parallel shards index their draws by the LOCAL row: give every rank its own Philox key so
                 # that row b of two shards never sees the same uniforms (ranks must still agree on the minibatch)
                 rng.seed = (rng.seed ^ (0x9E3779B97F4A7C15 * (self.dp.rank + 1))) & (2 ** 64 - 1)
@@ -331,6 +336,8 @@ class TrainFn:
         a.rng = rng
         a.cost_out = self.cost_dev.data_ptr() if costs is None else costs.data_ptr()
         a.path, a.tf32, a.phase = _lib.PATHS[self.path], int(self.tf32), phase
+        if comm is not None:
+            a.comm, a.B_total = comm.handle, int(rows_total)
         if phase != _lib.PHASE_FULL:
             a.stats_buf, a.B_total = self._stats.data_ptr(), int(rows_total)
             if a.path in (_lib.PATH_SKINNY, _lib.PATH_TINY) or phase == _lib.PHASE_APPLY:

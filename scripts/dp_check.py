@@ -1,4 +1,5 @@
-"""torchrun --nproc-per-node 2 scripts/dp_check.py : NCCL data-parallel CD step == single-GPU step,
+"""torchrun --nproc-per-node 2 scripts/dp_check.py : NCCL data-parallel CD step (mdbn_cd_args.comm; DP_HOST=1 for the
+host-level torch.distributed form) == single-GPU step,
 and modality-parallel MDBN pretraining == sequential (same weights)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,7 +24,7 @@ for path, tf32 in (("generic", False), ("tensor", True)):
     r = M.RBM(n_visible=V, n_hidden=H, W=W0, theano_rng=M.BufferStreams(lambda l, c, b: Uloc))
     cost, upd = r.get_cost_updates(lr=0.1, k=k, weightcost=0.0002, batch_size=B)
     fn = r.make_train_fn(data, cost, upd, path=path, tf32=tf32)
-    fn.dp = DataParallel()
+    fn.dp = DataParallel(c_abi=os.environ.get("DP_HOST") is None)      # default: the communicator inside libmdbn_b200.so
     c = fn(np.arange(B, dtype=np.int32), 0.5)
     # reference: the whole minibatch on this GPU alone
     r1 = M.RBM(n_visible=V, n_hidden=H, W=W0, theano_rng=M.BufferStreams(lambda l, c, b: U))

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.mdbn_abi_version() == 1
+    assert lib.mdbn_abi_version() == 2
     assert isinstance(lib.mdbn_last_error(), bytes)
     assert lib.mdbn_stats_size(784, 500) == 784 * 500 + 500 + 784 + 2
 
@@ -55,8 +55,9 @@ def test_struct_layout_matches_header():
 #include <stdio.h>
 #include <stddef.h>
 #include "mdbn_b200.h"
-int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(mdbn_rng), sizeof(mdbn_cd_args),
-  offsetof(mdbn_cd_args, rng), offsetof(mdbn_cd_args, cost_out), offsetof(mdbn_cd_args, B_total)); return 0; }
+int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mdbn_rng), sizeof(mdbn_cd_args),
+  offsetof(mdbn_cd_args, rng), offsetof(mdbn_cd_args, cost_out), offsetof(mdbn_cd_args, B_total),
+  offsetof(mdbn_cd_args, comm)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -65,7 +66,7 @@ int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(mdbn_rng), sizeof(mdbn_cd
                                os.path.join(d, "t")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [ctypes.sizeof(_lib.Rng), ctypes.sizeof(_lib.CdArgs), _lib.CdArgs.rng.offset,
-           _lib.CdArgs.cost_out.offset, _lib.CdArgs.B_total.offset]
+           _lib.CdArgs.cost_out.offset, _lib.CdArgs.B_total.offset, _lib.CdArgs.comm.offset]
     assert [int(x) for x in out] == got
 
 

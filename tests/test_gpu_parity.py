@@ -322,6 +322,77 @@ def test_standalone_training_vs_golden(name):
     close(r.vbias.get_value(), g["vbias"], rtol=5e-5, scale=max(np.abs(g["vbias"]).max(), 1e-3), what="vbias")
 
 
+# ---------------------------------------------------------------------------
+# the seven layers of the AML-shaped MDBN, 200 steps each, teacher-forced
+# ---------------------------------------------------------------------------
+AML_LAYERS = [
+    # name, kind, V, H, B, k, lr, momentum, lambda_1, lambda_2, weightcost   (src/AMLsm.py:38-62, src/dbn.py:284-294)
+    ("ME_559x40_cd10", O.GRBM, 559, 40, 20, 10, 0.005, 0.0, 0.01, 0.01, 0.0),
+    ("GE_19937x400", O.GRBM, 19937, 400, 20, 1, 0.005, 0.0, 0.01, 0.1, 0.0),
+    ("GE_400x40", O.RBM, 400, 40, 20, 1, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("SM_1686x200", O.GRBM, 1686, 200, 20, 1, 0.005, 0.0, 0.01, 0.01, 0.0),
+    ("SM_200x20", O.RBM, 200, 20, 20, 1, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("top_100x24", O.RBM, 100, 24, 20, 1, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("top_24x3", O.RBM, 24, 3, 20, 1, 0.1, 0.6, 0.0, 0.0, 0.0002),
+]
+
+
+@pytest.mark.parametrize("cfg", AML_LAYERS, ids=[c[0] for c in AML_LAYERS])
+def test_aml_layers_200_steps_teacher_forced(cfg):
+    """Every layer of the AML-shaped MDBN for 200 consecutive CD steps under the shared random buffer against the
+    float64 oracle.  Teacher-forced: before each step both sides start from the oracle's state rounded to fp32 (one
+    flipped Bernoulli bit would otherwise change everything downstream), so every single step is held to
+    the bar: regularised gradient (= the new speed) 3e-5, parameters 1e-5, cost 2e-4."""
+    name, kind, V, H, B, k, lr, mom, l1, l2, wc = cfg
+    m = M()
+    n_steps, N = 200, 170
+    data = synth(kind, N, V, seed=len(name))
+    if kind == O.RBM:
+        data = np.random.RandomState(3).rand(N, V).astype(np.float32)        # upper layers see sigmoid means in (0,1)
+    L = O.Layer(V, H, kind, numpy_rng=np.random.RandomState(123), dtype=np.float64)
+    L.W[...] = L.W.astype(np.float32)
+    W0 = L.W.copy()
+    prov = lambda layer, call, b: shared_u.step_buffer(7, layer, call, kind, True, b, V, H, k)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    r = cls(n_visible=V, n_hidden=H, W=W0.astype(np.float32), theano_rng=m.BufferStreams(prov))
+    cost, upd = r.get_cost_updates(lr=lr, k=k, lambda_1=l1, lambda_2=l2, weightcost=wc, batch_size=B)
+    fn = r.make_train_fn(data, cost, upd)
+    rs = np.random.RandomState(11)
+    worst = dict(W=0.0, S=0.0, c=0.0)
+    state = ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed")
+    for t in range(n_steps):
+        idx = rs.permutation(N)[:B].astype(np.int32)
+        for nm in state:                                  # teacher forcing: the oracle's state, fp32-rounded, on both sides
+            a = getattr(L, nm)
+            a[...] = a.astype(np.float32)
+            if t > 0:
+                getattr(r, nm).set_value(a.astype(np.float32))
+        c = fn(idx, mom)
+        U, tr = prov(0, t, B), {}
+        co = O.cd_step(L, data[idx].astype(np.float64), U, lr=lr, k=k, lambda_1=l1, lambda_2=l2,
+                       weightcost=wc, batch_size=B, momentum=mom, W_snap=W0, trace=tr)
+        # a Bernoulli draw closer to its probability than the tolerance may legitimately flip in fp32 (north star):
+        # such a step is not compared (teacher forcing re-aligns both sides at the next one)
+        u = O._views(np.asarray(U), kind, True, B, V, H, k)
+        margin = np.abs(u["hpos"] - tr["ph_mean"]).min()
+        for s_ in range(k):
+            if ("v%d" % s_) in u and kind == O.RBM:
+                margin = min(margin, np.abs(u["v%d" % s_] - tr["chain"][s_]["nv_mean"]).min())
+            if s_ + 1 < k:
+                margin = min(margin, np.abs(u["h%d" % s_] - tr["chain"][s_]["nh_mean"]).min())
+        if margin < 1e-5:
+            worst["S"] += 1
+            continue
+        assert abs(c - co) <= 2e-4 * abs(co) + 1e-5, "step %d cost %r vs oracle %r" % (t, c, co)
+        if t % 10 == 9 or t < 3:                          # (device -> host copies of a 32 MB layer every step are the test's cost)
+            close(r.W_speed.get_value(), L.W_speed, rtol=3e-5, scale=np.abs(L.W_speed).max(), what="W_speed step %d" % t)
+            close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W step %d" % t)
+            close(r.hbias.get_value(), L.hbias, rtol=3e-5, scale=max(np.abs(L.hbias).max(), 1e-4), what="hbias step %d" % t)
+            close(r.vbias.get_value(), L.vbias, rtol=3e-5, scale=max(np.abs(L.vbias).max(), 1e-4), what="vbias step %d" % t)
+        worst["c"] = max(worst["c"], abs(c - co) / (abs(co) + 1e-12))
+    assert worst["S"] <= n_steps // 4, "too many steps excluded for near-ties: %d" % worst["S"]
+
+
 def test_philox_sampling_statistics_and_determinism():
     m = M()
     V, H, B = 64, 4096, 64
@@ -535,6 +606,42 @@ def test_step_from_host_equals_device_resident(kind, pcd):
            for i in range(n_mb)]
     assert got[0] is None and got[1:] == want[:-1] and fn_lag.flush() == want[-1] and fn_lag.flush() is None
     assert np.array_equal(r_ref.W.get_value(), r_lag.W.get_value())
+
+
+@pytest.mark.parametrize("kind,path,tf32,B,pcd", [(O.RBM, "generic", False, 48, False), (O.GRBM, "tensor", True, 64, False),
+                                                  (O.RBM, "tensor", True, 64, True)])
+def test_c_abi_communicator_step_equals_full_step(kind, path, tf32, B, pcd):
+    """The data-parallel step INSIDE the library (mdbn_cd_args.comm: shard statistics -> NCCL all-reduce in two chunks
+    on a side stream -> update) on a one-rank communicator == the plain full step: unique id, mdbn_comm_init, the
+    event choreography between the caller's stream and the collective stream, B_total, mdbn_comm_destroy.
+    (Two ranks need two GPUs: scripts/dp_check.py under torchrun; the sum over shards is covered by
+    test_stats_apply_phases_equal_full_step and by the gloo test of the host logic.)"""
+    from mdbn_b200.parallel import DataParallel
+    m = M()
+    V, H, k = 200, 72, 2
+    data = synth(kind, 2 * B, V, seed=23)
+    cls = m.GRBM if kind == O.GRBM else m.RBM
+    W0 = O.init_W(np.random.RandomState(4), V, H).astype(np.float32)
+
+    def make(dp):
+        r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(77))
+        P = m.shared(np.zeros((B, H), np.float32)) if pcd else None
+        cost, upd = r.get_cost_updates(lr=0.05, k=k, lambda_1=0.01, lambda_2=0.1, weightcost=0.0002, batch_size=B, persistent=P)
+        fn = r.make_train_fn(data, cost, upd, path=path, tf32=tf32)
+        if dp:
+            fn.dp = DataParallel(c_abi=True)
+            assert fn.dp.comm is not None and fn.dp.world == 1
+        return r, fn
+    r1, f1 = make(False)
+    r2, f2 = make(True)
+    for t in range(3):
+        idx = np.arange(t % 2 * B, (t % 2 + 1) * B, dtype=np.int32)
+        c1, c2 = f1(idx, 0.5), f2(idx, 0.5)
+        assert abs(c1 - c2) <= 1e-6 * abs(c1) + 1e-7, (t, c1, c2)
+    for name in ("W", "hbias", "vbias", "W_speed", "hbias_speed", "vbias_speed"):
+        a, b = getattr(r2, name).get_value(), getattr(r1, name).get_value()
+        close(a, b, rtol=1e-6, scale=max(np.abs(b).max(), 1e-4), what=name)
+    f2.dp.comm.close()
 
 
 # ---------------------------------------------------------------------------
