@@ -49,7 +49,7 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a, bool chain = fals
   if (g.CQ > NT) return g;
   if (g.CQ <= 32) { g.GW = 1; while (g.GW < g.CQ) g.GW <<= 1; } else g.GW = (g.CQ + 31) / 32 * 32;
   g.G = NT / g.GW;
-  g.grid = c->num_sms;
+  g.grid = c->num_sms;      // (fewer, fatter CTAs on small layers measured SLOWER: the per-CTA O(B*H) flush and rebuild stay)
   if (g.BT * g.CQ > g.grid * NT || g.grid < g.BT || a.ldw > 4 * NT) return g;
   g.rows_per_cta = (a.V + g.grid - 1) / g.grid;
   g.rows_small = g.rows_per_cta;
@@ -163,7 +163,8 @@ int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_
   // scratch: two sets of 5 fixed-point accumulators [BT][ldw] + cost partials.  A launch works in one set
   // (zero on entry) and clears the other; everything is re-zeroed when the layout changes.
   const size_t n_acc = (size_t)g.BT * a.ldw;
-  const size_t total_b = 2 * 5 * n_acc * sizeof(unsigned long long) + ((size_t)g.grid + 64 + n_acc) * sizeof(float);
+  const size_t n_cost = ((size_t)g.grid + 64 + 3) & ~(size_t)3;     // keeps PHf 16-byte aligned whatever the SM count
+  const size_t total_b = 2 * 5 * n_acc * sizeof(unsigned long long) + (n_cost + n_acc) * sizeof(float);
   mdbn_ctx::Buf& wb = c->ws[WS_SKINNY];
   const void* before = wb.p;
   const size_t before_n = wb.n;
@@ -182,7 +183,7 @@ int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_
   c->skinny_parity = (c->skinny_parity + (unsigned)n_steps) & 1u;
   p.n_steps = n_steps;
   p.cost_part = reinterpret_cast<float*>(base + 2 * 5 * n_acc);
-  p.PHf = p.cost_part + g.grid + 64;
+  p.PHf = p.cost_part + n_cost;
   p.bar = reinterpret_cast<unsigned long long*>(c->barrier);
   static const bool want_timing = getenv("MDBN_SKINNY_TIMING") != nullptr;
 #ifdef MDBN_SKINNY_DEBUG
