@@ -122,8 +122,10 @@ int skinny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_
   sk::Geometry g = sk::plan(c, a, n_steps > 1);
   MDBN_CHECK(n_steps >= 1, "skinny path: n_steps must be >= 1");
   MDBN_CHECK(n_steps == 1 || a.rng.mode == MDBN_RNG_PHILOX, "skinny path: multi-step launches need the PHILOX generator");
-  if (!g.ok && n_steps > 1 && sk::plan(c, a, false).ok) {
-    // the second slab set of the fused chain does not fit next to this layer's tiles: one launch per step
+  if (n_steps > 1 && ((!g.ok && sk::plan(c, a, false).ok) || (g.ok && g.BT > 10 && (size_t)a.V * a.ldw * 4 > ((size_t)8 << 20)))) {
+    // one launch per step when the second slab set of the fused chain does not fit next to this layer's tiles, and
+    // for B > 10 on large layers, where the looped instantiation cannot fuse (register budget) and measures slower
+    // than single launches (19937x400, B = 20: 129 vs 121 us per step; small layers still gain from one launch)
     for (int s = 0; s < n_steps; ++s) {
       mdbn_cd_args one = a;
       one.indices = a.indices ? a.indices + (size_t)s * a.B : nullptr;

@@ -789,15 +789,17 @@ __global__ void __launch_bounds__(nt_of(BT), 1) cd_skinny_kernel(const __grid_co
 #pragma unroll
           for (int b = 0; b < BT; ++b) da2[b] = db2[b] = 0ULL;
           const uint32_t s_hs = smem_u32(hs);
-          // a warp takes whole boxes; its half-warps take ADJACENT 16-byte chunks of a box, so the two h addresses of
-          // a broadcast load fall into one 128-byte line (one wavefront; different boxes would conflict: two)
-          for (int bx = warp; bx < nbox; bx += NWARP) {
+          // Work unit = one PAIR of adjacent 16-byte chunks of a box (its half-warps take one chunk each, so the two h
+          // addresses of a broadcast load fall into one 128-byte line: one wavefront; different boxes would conflict).
+          // The 4 * nbox units go round-robin over the warps: 52 units on 8 warps = 7,7,7,7,6,6,6,6 — and every
+          // scheduler (warps w and w+4) gets 13, where whole boxes gave 16 / 12 / 12 / 12.
+          // NOT unrolled: straight-line code this long is bound by instruction fetch (ncu: stall_no_instruction)
+#pragma unroll 1
+          for (int u = warp; u < 4 * nbox; u += NWARP) {
+            const int bx = u >> 2, c2 = u & 3;
             const uint32_t bpa = smem_u32(tile) + bx * box_bytes + lr * 128;
             const uint32_t hb0 = s_hs + bx * 128;
-            // NOT fully unrolled: a box is visited once per tile, straight-line code this long is bound by
-            // instruction fetch (ncu: stall_no_instruction); the 2-chunk body is re-run from the i-cache
-#pragma unroll 2
-            for (int c2 = 0; c2 < 4; ++c2) {
+            {
               const int c = 2 * c2 + half;
               const uint32_t sw = (c ^ (lr & 7)) << 4;                             // rows l and l+16 swizzle alike
               const ulonglong2 wa = lds128(bpa + sw), wb = lds128(bpa + 16 * 128 + sw);
