@@ -343,6 +343,20 @@ __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long 
     if (xi) xi[b * ldo + i] = roundf(x);
   }
 }
+// the same, four columns per thread (V, strides and pointers multiples of 4 / 16 bytes): one row per blockIdx.y
+__global__ void gather_rows_ld4_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
+                                       int V4, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
+  const int b = blockIdx.y;
+  const long long r = idx ? idx[b] : b;
+  const float4* src = reinterpret_cast<const float4*>(data + r * ld);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)b * ldo);
+  float4* dx = xi ? reinterpret_cast<float4*>(xi + (size_t)b * ldo) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V4; i += gridDim.x * blockDim.x) {
+    const float4 x = __ldg(src + i);
+    dst[i] = x;
+    if (dx) dx[i] = make_float4(roundf(x.x), roundf(x.y), roundf(x.z), roundf(x.w));
+  }
+}
 // raw column sums of (top half - bottom half) of a [2B, N] matrix, two deterministic stages:
 // row chunks in parallel, then a fixed-order sum of the chunk partials
 __global__ void col_diff_partial_kernel(const float* __restrict__ X, long long ld, int B, int N, int rows_per_chunk,
@@ -355,18 +369,19 @@ __global__ void col_diff_partial_kernel(const float* __restrict__ X, long long l
   partial[(size_t)blockIdx.y * N + n] = p - q;
 }
 __global__ void col_diff_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // one warp per column
   if (n >= N) return;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * N + n];
-  out[n] = s;
+  for (int c = lane; c < chunks; c += 32) s += partial[(size_t)c * N + n];
+  s = warp_sum(s);
+  if (lane == 0) out[n] = s;
 }
 static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int N, float* out, cudaStream_t st) {
   const int rpc = 32, chunks = (B + rpc - 1) / rpc;
   float* part = (float*)ws_get(c, WS_MISC, (size_t)chunks * N * sizeof(float));
   if (!part) return 3;
   col_diff_partial_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, st>>>(X, ld, B, N, rpc, part);
-  col_diff_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, chunks, N, out);
+  col_diff_final_kernel<<<(N + 7) / 8, 256, 0, st>>>(part, chunks, N, out);
   c->launches += 2;
   return 0;
 }
@@ -491,7 +506,10 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   MDBN_CHECK(G != nullptr, "cd_step: stats buffer missing");
   float* XV = (float*)ws_get(c, WS_XV, (size_t)2 * B * ldx * sizeof(float));
   float* YH = (float*)ws_get(c, WS_YH, (size_t)2 * B * ldy * sizeof(float));
-  float* HS = (float*)ws_get(c, WS_HS, (size_t)B * ldy * sizeof(float));
+  // PCD chain state: the caller's [B, H] array IS the chain buffer when its row stride suits TMA (H % 4 == 0, 16-byte
+  // aligned): the Gibbs steps read and overwrite it in place, no copy in, no copy out (src/rbm.py:308-311, :369)
+  const bool chain_in_place = a.persistent != nullptr && ldy == H && (((uintptr_t)a.persistent) & 15) == 0;
+  float* HS = chain_in_place ? a.persistent : (float*)ws_get(c, WS_HS, (size_t)B * ldy * sizeof(float));
   float* VS = (float*)ws_get(c, WS_VS, (size_t)B * ldx * sizeof(float));
   float* PREV = (float*)ws_get(c, WS_PREV, (size_t)B * ldx * sizeof(float));
   float* RED = (float*)ws_get(c, WS_RED, (size_t)(B > 4096 ? B : 4096) * sizeof(float));
@@ -505,15 +523,20 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   }
   ULayout ul = u_layout(a.kind, a.noisy, B, V, H);
   const int eb = 4 * c->num_sms;
-  gather_rows_ld_kernel<<<eb, 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V, XV, ldx, XI);
+  if (V % 4 == 0 && a.ld_data % 4 == 0 && (((uintptr_t)a.data) & 15) == 0)
+    gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, B), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V / 4, XV, ldx, XI);
+  else
+    gather_rows_ld_kernel<<<eb, 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V, XV, ldx, XI);
   c->launches++;
   // positive phase
   MDBN_TRY(up(c, a.W, a.ldw, a.hbias, B, V, H, XV, ldx, nullptr, YH, pcd ? nullptr : HS, ldy,
               make_seg(a.rng, ul.off_h0, 0), st));
   if (pcd) {
     MDBN_TRY(up(c, a.W, a.ldw, a.hbias, B, V, H, XI, ldx, PREX, nullptr, nullptr, ldy, make_seg(a.rng, 0, 0), st));
-    copy_rows_kernel<<<eb, 256, 0, st>>>(a.persistent, H, HS, ldy, B, H);      // chain state, padded stride for TMA
-    c->launches++;
+    if (!chain_in_place) {
+      copy_rows_kernel<<<eb, 256, 0, st>>>(a.persistent, H, HS, ldy, B, H);      // chain state, padded stride for TMA
+      c->launches++;
+    }
   }
   float* nv_mean = XV + (size_t)B * ldx;
   float* nh_mean = YH + (size_t)B * ldy;
@@ -554,8 +577,10 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     c->launches++;
     bump_bit_kernel<<<1, 32, 0, st>>>(a.bit_i_idx, V);
     c->launches++;
-    copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldy, a.persistent, H, B, H);
-    c->launches++;
+    if (!chain_in_place) {
+      copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldy, a.persistent, H, B, H);
+      c->launches++;
+    }
   } else {
     const int nb = 256;
     recon_cost_ld_kernel<<<nb, 256, 0, st>>>(PREV, XV, ldx, B, V, a.kind, RED);
