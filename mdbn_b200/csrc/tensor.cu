@@ -3,8 +3,8 @@
 //   tcgen05.mma.cta_group::1.kind::tf32  (one elected thread issues; SASS: UTCHMMA-family)
 //   operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle; UTMALDG)
 //   accumulator 128 x 128 fp32 in tensor memory (TMEM), read back with tcgen05.ld (LDTM)
-//   warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 =
-//   epilogue, 3-stage mbarrier ring, 2 CTAs per SM so one tile's epilogue overlaps another's mainloop.
+//   warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-9 =
+//   epilogue (two per TMEM lane quarter, one column half each; MUFU sigmoid), 3-stage mbarrier ring, 2 CTAs per SM so one tile's epilogue overlaps another's mainloop.
 //
 // The three GEMMs of a CD step map onto ONE kernel template by operand major-ness:
 //   propup    H[B,H]  = X[B,V] W[V,H]          A K-major  (X rows),  B MN-major (W rows are K)
@@ -26,7 +26,7 @@ namespace tc {
 constexpr int BM = 128, BN = 128, BK = 32;     // BK floats = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter: column halves)
 constexpr int TMEM_COLS = 128;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -45,6 +45,12 @@ struct EpiParams {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// sigmoid on the MUFU pipe (ex2.approx + rcp.approx, a few ulp — far inside the 2e-3 bar of the TF32 path)
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + __expf(-x)));
+  return r;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -190,9 +196,10 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;           // a warp may only touch its own 32 TMEM lanes
+    const int chalf = (warp - 2) >> 2;      // ... and the two warps of a quarter split the columns
     const int m = m0 + quarter * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
       const int nb = n0 + c * 32;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
                             __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w};
             float mu[4], x[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) mu[t] = ep.act == ACT_SIGMOID ? sigmoidf_(pre[t]) : pre[t];
+            for (int t = 0; t < 4; ++t) mu[t] = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre[t]) : pre[t];
             if (ep.pre) *reinterpret_cast<float4*>(ep.pre + m * ep.ld_pre + n) = make_float4(pre[0], pre[1], pre[2], pre[3]);
             if (ep.mean) *reinterpret_cast<float4*>(ep.mean + m * ep.ld_mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
             if (ep.sample) {
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
             const int n = nb + j;
             if (n < N) {
               const float pre = __uint_as_float(r[j]) + ep.bias[n];
-              const float mu = ep.act == ACT_SIGMOID ? sigmoidf_(pre) : pre;
+              const float mu = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre) : pre;
               if (ep.pre) ep.pre[m * ep.ld_pre + n] = pre;
               if (ep.mean) ep.mean[m * ep.ld_mean + n] = mu;
               if (ep.sample) {
