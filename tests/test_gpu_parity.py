@@ -322,8 +322,43 @@ def test_standalone_training_vs_golden(name):
     close(r.vbias.get_value(), g["vbias"], rtol=5e-5, scale=max(np.abs(g["vbias"]).max(), 1e-3), what="vbias")
 
 
+def test_philox_gaussian_moments_noisy_grbm():
+    """GRBM(error_free=False).sample_v_given_h draws v = mean + N(0,1) (src/rbm.py:650-658) with the in-kernel
+    Philox Box-Muller generator: the noise must be standard normal, independent across elements and calls, and
+    reproducible for a given seed — at a configuration shape (1686 visibles) and on both single-phase paths."""
+    m = M()
+    V, H, B = 1686, 200, 64
+    W0 = O.init_W(np.random.RandomState(2), V, H).astype(np.float32)
+    h = (np.random.RandomState(3).rand(B, H) < 0.5).astype(np.float32)
+
+    def draw(seed, n_calls=2):
+        r = m.GRBM(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(seed), error_free=False)
+        out = []
+        for _ in range(n_calls):
+            _, mean, smp = r.sample_v_given_h(h)
+            out.append((smp - mean).cpu().numpy().astype(np.float64))
+        return out, mean.cpu().numpy()
+    (n1, n2), mean = draw(5)
+    ref = h @ W0.T
+    close(mean, ref, rtol=1e-5, scale=np.abs(ref).max(), what="linear Gaussian mean")
+    for z in (n1, n2):
+        assert abs(z.mean()) < 4.0 / np.sqrt(z.size)                     # 4 sigma of the sample mean
+        assert abs(z.var() - 1.0) < 4.0 * np.sqrt(2.0 / z.size)
+        assert abs((z ** 3).mean()) < 4.0 * np.sqrt(15.0 / z.size)       # skewness ~ 0
+        assert abs((z ** 4).mean() - 3.0) < 4.0 * np.sqrt(96.0 / z.size)  # kurtosis ~ 3
+        assert abs(np.corrcoef(z[:, :-1].ravel(), z[:, 1:].ravel())[0, 1]) < 4.0 / np.sqrt(z.size)   # neighbours independent
+    assert abs(np.corrcoef(n1.ravel(), n2.ravel())[0, 1]) < 4.0 / np.sqrt(n1.size)                   # calls independent
+    (m1, m2), _ = draw(5)
+    assert np.array_equal(m1, n1) and np.array_equal(m2, n2)            # same seed, same program -> same draws
+    (k1, _k2), _ = draw(6)
+    assert not np.array_equal(k1, n1)
+
+
 # ---------------------------------------------------------------------------
 # the seven layers of the AML-shaped MDBN (SURVEY.md 8d config 4), 200 steps each, teacher-forced
+# (the two `top_*` rows are the layers MDBN.train_top builds, src/MDBN.py:31-42: its free-running golden run can only
+#  be tracked at 5e-2 over 800 iterations — one flipped Bernoulli bit decorrelates the tail — so the 1e-5 bar on them
+#  is held here, step by step)
 # ---------------------------------------------------------------------------
 AML_LAYERS = [
     # name, kind, V, H, B, k, lr, momentum, lambda_1, lambda_2, weightcost   (src/AMLsm.py:38-62, src/dbn.py:284-294)
