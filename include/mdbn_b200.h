@@ -65,6 +65,12 @@ int mdbn_propup(mdbn_ctx* ctx, const float* W, int ldw, const float* hbias,
                 float* pre_out, float* mean_out, float* sample_out,
                 const mdbn_rng* rng, void* stream);
 
+/* out = sigmoid(x W + b): the deterministic up-pass of one DBN layer (mean only, no sampling).
+ * replaces: HiddenLayer.output src/mlp.py:103-107 as used by DBN.get_output src/dbn.py:214-236 and by the input of the
+ *           upper layers during pretraining (src/dbn.py:146). */
+int mdbn_forward(mdbn_ctx* ctx, const float* W, int ldw, const float* b, const float* x, int ldx, int B, int V, int H,
+                 float* out, void* stream);
+
 /* pre = h W^T + vbias.
  * kind RBM : mean = sigmoid(pre), sample = (u < mean)              src/rbm.py:215-240
  * kind GRBM: mean = pre (linear, unit variance); sample = mean, or mean + n with

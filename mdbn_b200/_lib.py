@@ -42,7 +42,7 @@ class CdArgs(C.Structure):
 
 EXPORTS = ("mdbn_abi_version", "mdbn_last_error", "mdbn_create", "mdbn_destroy", "mdbn_launch_count",
            "mdbn_set_tf32_phases",
-           "mdbn_propup", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_copy_async", "mdbn_stats_size",
+           "mdbn_propup", "mdbn_forward", "mdbn_propdown", "mdbn_free_energy", "mdbn_cd_step", "mdbn_cd_steps", "mdbn_copy_async", "mdbn_stats_size",
            "mdbn_comm_unique_id", "mdbn_comm_init", "mdbn_comm_destroy", "mdbn_comm_all_reduce")
 COMM_ID_BYTES = 128
 
@@ -73,6 +73,7 @@ def load():
         lib.mdbn_stats_size.argtypes = [i, i]
         lib.mdbn_stats_size.restype = C.c_longlong
         lib.mdbn_propup.argtypes = [vp, vp, i, vp, vp, i, i, i, i, vp, vp, vp, C.POINTER(Rng), vp]
+        lib.mdbn_forward.argtypes = [vp, vp, i, vp, vp, i, i, i, i, vp, vp]
         lib.mdbn_propdown.argtypes = [vp, vp, i, vp, vp, i, i, i, i, i, i, vp, vp, vp, C.POINTER(Rng), vp]
         lib.mdbn_free_energy.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, i, i, vp, vp]
         lib.mdbn_cd_step.argtypes = [vp, C.POINTER(CdArgs), vp]

@@ -113,6 +113,12 @@ int mdbn_propup(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const 
                         make_seg(rng ? *rng : none, 0, 0), (cudaStream_t)stream);
 }
 
+int mdbn_forward(mdbn_ctx* c, const float* W, int ldw, const float* b, const float* x, int ldx, int B, int V, int H,
+                 float* out, void* stream) {
+  MDBN_CHECK(out != nullptr, "forward: out is NULL");
+  return mdbn_propup(c, W, ldw, b, x, ldx, B, V, H, nullptr, out, nullptr, nullptr, stream);
+}
+
 int mdbn_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vbias, const float* h, int ldh, int B, int V,
                   int H, int kind, int noisy, float* pre_out, float* mean_out, float* sample_out,
                   const mdbn_rng* rng, void* stream) {

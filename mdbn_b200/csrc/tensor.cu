@@ -290,9 +290,40 @@ static EncodeFn get_encode() {
   return fn;
 }
 
+// Encoding a tensor map costs the host 3-5 us, and a CD step issues 5 to 2k+3 GEMMs on the SAME operands step after step
+// (parameters, context scratch): a small per-thread cache keyed by everything that enters the descriptor.
+struct MapKey {
+  const float* ptr;
+  long long inner, outer, ld;
+  int box_inner, box_outer, mn;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && mn == o.mn;
+  }
+};
+struct MapCache {
+  static constexpr int N = 64;
+  MapKey key[N];
+  CUtensorMap map[N];
+  int used = 0, next = 0;
+};
+static int make_map_uncached(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long ld,
+                             int box_inner, int box_outer, bool mn_major);
 // operand matrix in memory: [outer][inner] row-major with row stride ld (floats)
 static int make_map(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long ld, int box_inner,
                     int box_outer, bool mn_major) {
+  static thread_local MapCache cache;
+  const MapKey kq{ptr, inner, outer, ld, box_inner, box_outer, mn_major ? 1 : 0};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == kq) { *tm = cache.map[i]; return 0; }
+  MDBN_TRY(make_map_uncached(tm, ptr, inner, outer, ld, box_inner, box_outer, mn_major));
+  const int slot = cache.used < MapCache::N ? cache.used++ : (cache.next++ % MapCache::N);
+  cache.key[slot] = kq;
+  cache.map[slot] = *tm;
+  return 0;
+}
+static int make_map_uncached(CUtensorMap* tm, const float* ptr, long long inner, long long outer, long long ld,
+                             int box_inner, int box_outer, bool mn_major) {
   EncodeFn enc = get_encode();
   MDBN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   MDBN_CHECK(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, "TMA operand must be 16-byte aligned (ptr %p ld %lld)",

@@ -38,11 +38,13 @@ class HiddenLayer(object):
         """sigmoid(x W + b) as a device tensor (src/mlp.py:103-107)."""
         x = as_device_matrix(x, self.device)
         out = torch.empty((x.shape[0], self.n_out), dtype=torch.float32, device=self.device)
-        pre = out if self.activation is None else None
-        mean = out if self.activation is not None else None
-        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-        _lib.check(self.ctx.lib.mdbn_propup(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
-                                            self.b.data.data_ptr(), x.data_ptr(), x.stride(0), x.shape[0],
-                                            self.n_in, self.n_out, vp(pre), vp(mean), None, None,
-                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.activation is not None:
+            _lib.check(self.ctx.lib.mdbn_forward(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
+                                                 self.b.data.data_ptr(), x.data_ptr(), x.stride(0), x.shape[0],
+                                                 self.n_in, self.n_out, out.data_ptr(), st))
+        else:
+            _lib.check(self.ctx.lib.mdbn_propup(self.ctx.handle, self.W.storage.data_ptr(), self.W.ld,
+                                                self.b.data.data_ptr(), x.data_ptr(), x.stride(0), x.shape[0],
+                                                self.n_in, self.n_out, ctypes.c_void_p(out.data_ptr()), None, None, None, st))
         return out
