@@ -28,7 +28,8 @@ typedef struct mdbn_comm mdbn_comm;   /* NCCL communicator of the data-parallel 
 enum { MDBN_RBM = 0, MDBN_GRBM = 1 };                       /* src/rbm.py:46 / :631 */
 enum { MDBN_RNG_NONE = 0, MDBN_RNG_BUFFER = 1, MDBN_RNG_PHILOX = 2 };
 /* AUTO picks by shape (full steps): TINY (one cluster, weights in shared memory: small layers), SKINNY (persistent
- * grid kernel, B <= 20), TENSOR (tcgen05 TF32 GEMMs, B % 32 == 0, needs tf32 = 1), else GENERIC (fp32 SIMT). */
+ * grid kernel, B <= 20), TENSOR (tcgen05 GEMMs with fused epilogues, any B > 20: fp32-exact split-TF32 arithmetic, or
+ * plain TF32 with tf32 = 1), else GENERIC (fp32 SIMT: operands that do not suit TMA). */
 enum { MDBN_PATH_AUTO = 0, MDBN_PATH_GENERIC = 1, MDBN_PATH_SKINNY = 2, MDBN_PATH_TENSOR = 3, MDBN_PATH_TINY = 4 };
 enum { MDBN_PHASE_FULL = 0, MDBN_PHASE_STATS = 1, MDBN_PHASE_APPLY = 2 };
 
@@ -52,8 +53,10 @@ int mdbn_create(mdbn_ctx** out, int device);
 int mdbn_destroy(mdbn_ctx* ctx);
 /* number of kernels this context has launched (diagnostic; bench.py's gpu_launches) */
 unsigned long long mdbn_launch_count(const mdbn_ctx* ctx);
-/* enable != 0: the single-phase calls below (propup / propdown) run on the tcgen05 TF32 tensor-core
- * path (tolerance 2e-3) instead of the fp32 path, when their operands are 16-byte aligned */
+/* The single-phase calls below (propup / propdown / free_energy / forward) run on the tcgen05 tensor-core path
+ * when their operands are 16-byte aligned (row strides multiples of 4) and the layer has >= 4096 weights:
+ * fp32-exact split-TF32 arithmetic by default (tolerance 1e-5); enable != 0 selects plain TF32 (tolerance 2e-3,
+ * one MMA per k-step instead of three). */
 int mdbn_set_tf32_phases(mdbn_ctx* ctx, int enable);
 
 /* pre = v W + hbias ; mean = sigmoid(pre) ; sample = (u < mean).  Any of the three
@@ -113,7 +116,8 @@ typedef struct {
   mdbn_rng rng;
   float* cost_out;       /* device float: reconstruction cost (CD) / pseudo-likelihood (PCD) */
   int path;              /* MDBN_PATH_* (AUTO picks by shape) */
-  int tf32;              /* allow the TF32 tensor-core path (tolerance 2e-3) */
+  int tf32;              /* TENSOR path arithmetic: 0 = fp32-exact split TF32 (three MMAs per k-step, tolerance 1e-5),
+                            1 = plain TF32 (tolerance 2e-3) */
   int phase;             /* MDBN_PHASE_FULL, or STATS (fill stats_buf, no update) / APPLY (update from stats_buf) */
   float* stats_buf;      /* data-parallel packing: [sum v0^T ph - nv^T nh (V*H) | sum(ph-nh) (H) | sum(v0-nv) (V) |
                             cost numerator (1) | rows (1)], raw sums over this rank's rows */

@@ -107,7 +107,8 @@ class Context:
         self.handle = h
 
     def set_tf32_phases(self, enable):
-        """Single-phase calls (propup/propdown/sample_*) on the tcgen05 TF32 path (tolerance 2e-3)."""
+        """Single-phase calls (propup/propdown/sample_*/free_energy) run on the tcgen05 path in fp32-exact
+        split-TF32 arithmetic by default; enable=True selects plain TF32 (tolerance 2e-3)."""
         check(self.lib.mdbn_set_tf32_phases(self.handle, int(bool(enable))))
 
     @property

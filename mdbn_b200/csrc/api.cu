@@ -90,6 +90,11 @@ int mdbn_set_tf32_phases(mdbn_ctx* c, int enable) {
 
 long long mdbn_stats_size(int V, int H) { return (long long)V * H + H + V + 2; }
 
+// The single-phase calls run on the tensor cores (fp32-exact split-TF32 by default, plain TF32 after
+// mdbn_set_tf32_phases) whenever the operands suit TMA; layers of a few thousand weights stay on the SIMT kernels
+// (one small launch either way).
+static bool tensor_phase_wanted(int V, int H) { return (long long)V * H >= 4096; }
+
 static int check_common(const mdbn_ctx* c, const void* W, int ldw, int B, int V, int H) {
   MDBN_CHECK(c != nullptr, "ctx is NULL");
   MDBN_CHECK(W != nullptr, "W is NULL");
@@ -106,7 +111,7 @@ int mdbn_propup(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const 
   MDBN_CHECK(!(rng && rng->mode == MDBN_RNG_BUFFER && sample_out) || rng->buffer, "propup: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
-  if (c->tf32_phases && tensor_phase_supported(W, ldw, v, ldv))
+  if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, v, ldv))
     return tensor_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
                          make_seg(rng ? *rng : none, 0, 0), (cudaStream_t)stream);
   return generic_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
@@ -130,7 +135,7 @@ int mdbn_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vbias, cons
   MDBN_CHECK(!(needs_rng && rng->mode == MDBN_RNG_BUFFER) || rng->buffer, "propdown: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
-  if (c->tf32_phases && tensor_phase_supported(W, ldw, h, ldh))
+  if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, h, ldh))
     return tensor_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
                            make_seg(rng ? *rng : none, 0, 1), (cudaStream_t)stream);
   return generic_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
@@ -142,6 +147,8 @@ int mdbn_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hbias, c
   MDBN_TRY(check_common(c, W, ldw, B, V, H));
   MDBN_CHECK(hbias && vbias && v && F_out && ldv >= V, "free_energy: bad arguments");
   MDBN_CUDA(cudaSetDevice(c->device));
+  if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, v, ldv))
+    return tensor_free_energy(c, W, ldw, hbias, vbias, v, ldv, B, V, H, kind, F_out, (cudaStream_t)stream);
   return generic_free_energy(c, W, ldw, hbias, vbias, v, ldv, B, V, H, kind, F_out, (cudaStream_t)stream);
 }
 
@@ -172,7 +179,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   if (path == MDBN_PATH_AUTO) {
     if (a->phase == MDBN_PHASE_FULL && tiny_supported(c, *a)) path = MDBN_PATH_TINY;
     else if (a->phase == MDBN_PHASE_FULL && skinny_supported(c, *a)) path = MDBN_PATH_SKINNY;
-    else if (a->tf32 && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;
+    else if ((a->B > 20 || a->tf32) && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;   // fp32-exact unless tf32
     else path = MDBN_PATH_GENERIC;
   }
   switch (path) {

@@ -95,10 +95,27 @@ int tensor_propup(mdbn_ctx*, const float* W, int ldw, const float* hb, const flo
                   float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
 int tensor_propdown(mdbn_ctx*, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
                     int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st);
+int tensor_free_energy(mdbn_ctx*, const float* W, int ldw, const float* hb, const float* vb, const float* v, int ldv,
+                       int B, int V, int H, int kind, float* F, cudaStream_t st);
 int apply_update(mdbn_ctx* c, const mdbn_cd_args& a, const float* G, int rows, cudaStream_t st);
 
 // ---- data-parallel step over NCCL: comm.cu ----
 int comm_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st);
+
+// hyper-parameters of the W / W_speed update (src/rbm.py:347-365) as the kernels take them
+struct UpdateScalars {
+  float inv_bnom, wc, c1 /*2*lr*lambda_1*/, decay /*1-2*lr*lambda_2*/, mom, lr;
+};
+inline UpdateScalars make_update_scalars(const mdbn_cd_args& a) {
+  UpdateScalars u;
+  u.inv_bnom = 1.0f / (float)a.B_nom;
+  u.wc = a.weightcost;
+  u.c1 = (2.0f * a.lr) * a.lambda_1;
+  u.decay = 1.0f - (2.0f * a.lr) * a.lambda_2;
+  u.mom = a.momentum;
+  u.lr = a.lr;
+  return u;
+}
 
 // layout of the App. A random buffer
 struct ULayout {

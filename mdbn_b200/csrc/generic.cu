@@ -186,6 +186,15 @@ __global__ void free_energy_kernel(const float* __restrict__ part, int splits, i
   if (threadIdx.x == 0) F[b] = kind == MDBN_GRBM ? -hid + vis : -hid - vis;
 }
 
+// (the tcgen05 path produces the same [splits][B][H] partials)
+int free_energy_from_parts(mdbn_ctx* c, const float* part, int splits, int B, int H, const float* hb, const float* v,
+                           long long ldv, int V, const float* vb, int kind, float* F, cudaStream_t st) {
+  free_energy_kernel<<<B, 256, 0, st>>>(part, splits, B, H, hb, v, ldv, V, vb, kind, F);
+  c->launches++;
+  MDBN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int generic_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hb, const float* vb, const float* v,
                         int ldv, int B, int V, int H, int kind, float* F, cudaStream_t st) {
   int splits = pick_splits(c, B, H, V);
@@ -281,10 +290,6 @@ __global__ void bump_bit_idx_kernel(int* bit_idx, int V) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *bit_idx = (*bit_idx + 1) % V;
 }
 
-struct UpdateScalars {
-  float inv_bnom, wc, c1 /*2*lr*lambda_1*/, decay /*1-2*lr*lambda_2*/, mom, lr;
-};
-
 // W, S update (src/rbm.py:347-365); G holds raw v0^T ph - nv^T nh sums, dense ld = H
 __global__ void update_w_kernel(float* __restrict__ W, float* __restrict__ S, const float* __restrict__ Wsnap,
                                 int ldw, const float* __restrict__ G, int V, int H, UpdateScalars u) {
@@ -319,13 +324,7 @@ __global__ void finalize_cost_kernel(const float* __restrict__ num, float inv_de
 
 int apply_update(mdbn_ctx* c, const mdbn_cd_args& a, const float* G, int rows, cudaStream_t st) {
   const int V = a.V, H = a.H;
-  UpdateScalars u;
-  u.inv_bnom = 1.0f / (float)a.B_nom;
-  u.wc = a.weightcost;
-  u.c1 = (2.0f * a.lr) * a.lambda_1;
-  u.decay = 1.0f - (2.0f * a.lr) * a.lambda_2;
-  u.mom = a.momentum;
-  u.lr = a.lr;
+  const UpdateScalars u = make_update_scalars(a);
   long long total = (long long)V * H;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 8 * c->num_sms) blocks = 8 * c->num_sms;

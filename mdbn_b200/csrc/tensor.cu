@@ -1,36 +1,52 @@
-// Large-batch / many-chain path: TF32 GEMMs on the 5th-generation tensor cores.
+// Batch > 20 path (mid batch, large batch, many chains): the GEMMs of a CD step on the 5th-generation tensor cores.
 //
 //   tcgen05.mma.cta_group::1.kind::tf32  (one elected thread issues; SASS: UTCHMMA-family)
 //   operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle; UTMALDG)
 //   accumulator 128 x 128 fp32 in tensor memory (TMEM), read back with tcgen05.ld (LDTM)
-//   warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-9 =
-//   epilogue (two per TMEM lane quarter, one column half each; MUFU sigmoid), 3-stage mbarrier ring, 2 CTAs per SM so one tile's epilogue overlaps another's mainloop.
+//   warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-9 = epilogue (two per TMEM
+//   lane quarter, one column half each; MUFU sigmoid), 3-stage mbarrier ring.
 //
 // The three GEMMs of a CD step map onto ONE kernel template by operand major-ness:
 //   propup    H[B,H]  = X[B,V] W[V,H]          A K-major  (X rows),  B MN-major (W rows are K)
 //   propdown  V[B,V]  = Hs[B,H] W[V,H]^T       A K-major,            B K-major  (W rows are N)
 //   stats     G[V,H]  = [v0;nv]^T [ph;nh] with the nv/nh half negated through the
 //             instruction descriptor's a_negate bit     A MN-major,  B MN-major, K = 2B
-// with the bias + sigmoid (or linear GRBM mean) + Bernoulli / Gaussian sampling fused into the
-// TMEM epilogue, so pre-activations never go to HBM.  TF32 keeps 10 mantissa bits of W and of
-// real-valued activations; {0,1} samples are exact.  Tolerance bar: 2e-3 relative.
+// with the bias + sigmoid (or linear GRBM mean) + Bernoulli / Gaussian sampling fused into the TMEM epilogue of the
+// first two (pre-activations never go to HBM) and the lambda_1 / lambda_2 / weight-cost / momentum update of W and
+// W_speed fused into the epilogue of the third (EPI_UPDATE: the statistics never go to HBM either, src/rbm.py:347-365).
+//
+// Two arithmetic modes (template parameter SPLIT):
+//   SPLIT = false  plain TF32: the tensor core truncates the fp32 operands to 10 mantissa bits.  Bar 2e-3, {0,1}
+//                  samples exact.  96 KB of stages -> 2 CTAs per SM (one tile's epilogue overlaps another's mainloop).
+//   SPLIT = true   fp32-exact ("3xTF32"): every real-valued operand tile gets a lo twin  x - trunc_tf32(x)  written
+//                  next to it in shared memory by the eight epilogue warps (idle during the mainloop) and each k-step
+//                  issues A*B + A_lo*B + A*B_lo into the same accumulator; {0,1} operands need no twin.  Error
+//                  ~2^-22 relative to sum|terms| -> the 1e-5 bar of the fp32 paths.  This is the DEFAULT for B > 20
+//                  (the W-streaming SIMT kernel's register budget ends at B = 20); tf32 = 1 selects the plain mode.
+// Skinny shapes (B <= 128 rows against 10^4 visible units) split K over the SMs: partial tiles, then one kernel
+// that sums them in fixed order and applies the same fused epilogue.
 #include <cuda.h>
 #include "ctx.h"
 
 namespace mdbn {
 
 int apply_update(mdbn_ctx* c, const mdbn_cd_args& a, const float* G, int rows, cudaStream_t st);   // generic.cu
+int free_energy_from_parts(mdbn_ctx* c, const float* part, int splits, int B, int H, const float* hb, const float* v,
+                           long long ldv, int V, const float* vb, int kind, float* F, cudaStream_t st);   // generic.cu
 
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;     // BK floats = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+constexpr int LO_OFF = A_BYTES + B_BYTES;      // SPLIT: the lo twins of A and B sit behind the pair
+__host__ __device__ constexpr int stage_bytes(bool split) { return (A_BYTES + B_BYTES) * (split ? 2 : 1); }
+__host__ __device__ constexpr int smem_bytes(bool split) { return STAGES * stage_bytes(split) + 1024 /*align*/ + 256 /*barriers*/; }
 constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter: column halves)
+constexpr int NEPI = NTHREADS - 64;
 constexpr int TMEM_COLS = 128;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-enum { EPI_ACT = 0, EPI_PART = 1 };
+enum { EPI_ACT = 0, EPI_PART = 1, EPI_UPDATE = 2 };
 enum { ACT_SIGMOID = 0, ACT_LINEAR = 1 };
 enum { SMP_NONE = 0, SMP_BERNOULLI = 1, SMP_MEAN = 2, SMP_GAUSS = 3 };
 
@@ -42,6 +58,11 @@ struct EpiParams {
   long long ld_pre, ld_mean, ld_sample;
   float* part;          // EPI_PART: [splits][M][N]
   int vec4;             // all epilogue pointers 16-byte aligned, strides and N multiples of 4
+  // EPI_UPDATE: the accumulator tile is v0^T ph - nv^T nh of rows m (visible) x columns n (hidden)
+  float *uW, *uS;
+  const float* uSnap;
+  int uldw;
+  UpdateScalars u;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,24 +140,93 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, bool a_n
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---- the fused epilogue of propup / propdown for 4 consecutive columns (n % 4 == 0, all pointers 16-byte aligned)
+//      and for one element; shared by the TMEM epilogue and by the split-K reduction kernel ----
+__device__ __forceinline__ void epi_quad(const EpiParams& ep, int m, int n, int N, const float (&acc)[4]) {
+  const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n);
+  const float pre[4] = {acc[0] + bv.x, acc[1] + bv.y, acc[2] + bv.z, acc[3] + bv.w};
+  float mu[4], x[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) mu[t] = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre[t]) : pre[t];
+  if (ep.pre) *reinterpret_cast<float4*>(ep.pre + m * ep.ld_pre + n) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+  if (ep.mean) *reinterpret_cast<float4*>(ep.mean + m * ep.ld_mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+  if (ep.sample) {
+    const long long e = (long long)m * N + n;      // multiple of 4 on this path: one Philox block feeds 4 draws
+    if (ep.smp == SMP_BERNOULLI) {
+      float u[4];
+      if (ep.rs.mode == MDBN_RNG_BUFFER) {
+        const float4 uv = __ldg(reinterpret_cast<const float4*>(ep.rs.seg + e));
+        u[0] = uv.x; u[1] = uv.y; u[2] = uv.z; u[3] = uv.w;
+      } else {
+        Philox4 ph = philox4x32_10((uint32_t)(e >> 2), ep.rs.c1, ep.rs.c2, ep.rs.c3, ep.rs.k0, ep.rs.k1);
+        u[0] = u24(ph.x); u[1] = u24(ph.y); u[2] = u24(ph.z); u[3] = u24(ph.w);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) x[t] = u[t] < mu[t] ? 1.f : 0.f;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) x[t] = ep.smp == SMP_GAUSS ? mu[t] + rng_normal(ep.rs, e + t) : mu[t];
+    }
+    *reinterpret_cast<float4*>(ep.sample + m * ep.ld_sample + n) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+}
+__device__ __forceinline__ void epi_one(const EpiParams& ep, int m, int n, int N, float acc) {
+  const float pre = acc + ep.bias[n];
+  const float mu = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre) : pre;
+  if (ep.pre) ep.pre[m * ep.ld_pre + n] = pre;
+  if (ep.mean) ep.mean[m * ep.ld_mean + n] = mu;
+  if (ep.sample) {
+    const long long e = (long long)m * N + n;
+    float x;
+    if (ep.smp == SMP_BERNOULLI) x = rng_uniform(ep.rs, e) < mu ? 1.f : 0.f;
+    else if (ep.smp == SMP_GAUSS) x = mu + rng_normal(ep.rs, e);
+    else x = mu;
+    ep.sample[m * ep.ld_sample + n] = x;
+  }
+}
+// W, W_speed update of one element from its raw statistic g = (v0^T ph - nv^T nh)[i][j]   src/rbm.py:347-365, :411-415
+__device__ __forceinline__ void update_one(const UpdateScalars& u, float graw, float w, float s, float snap, bool has_snap,
+                                           float& w_out, float& s_out) {
+  float g = graw * u.inv_bnom;
+  if (has_snap) g -= u.wc * snap;
+  float mult = u.decay;
+  if (u.c1 != 0.f) {
+    const float D = 1.0f + u.c1 / (fabsf(w) + 0.001f);
+    g = g / D;
+    mult = u.decay / D;
+  }
+  s_out = g + (s - g) * u.mom;
+  w_out = w * mult + s * u.lr;     // OLD speed: Theano updates are simultaneous (App. C-1)
+}
+
+// lo_mask (SPLIT only): bit 0 = A has a lo twin (real-valued operand), bit 1 = B has one
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                                                           int kb_per_split, int kb_neg, EpiParams ep) {
+                                                           int kb_per_split, int kb_neg, int lo_mask, EpiParams ep) {
+  constexpr int STAGE_BYTES = stage_bytes(SPLIT);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), ready0 = smem_u32(bars + 2 * STAGES),
+                 tfull = smem_u32(bars + 3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb_total = (K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(nkb_total, kb_begin + kb_per_split);
   const int nkb = kb_end - kb_begin;
+  const bool twins = SPLIT && lo_mask != 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(ready0 + 8 * s, NEPI / 32);      // one arrival per transform warp
+    }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
       mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
       const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
       const uint32_t bar = full0 + 8 * s;
-      mbar_expect_tx(bar, STAGE_BYTES);
+      mbar_expect_tx(bar, A_BYTES + B_BYTES);
       const int k0 = (kb_begin + i) * BK;
       if (A_MN) {
 #pragma unroll
@@ -177,22 +267,51 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
     // ===== MMA issuer =====
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES, it = i / STAGES;
-      mbar_wait(full0 + 8 * s, it & 1);
+      mbar_wait((twins ? ready0 : full0) + 8 * s, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
       const uint32_t idesc = make_idesc(A_MN, B_MN, (kb_begin + i) >= kb_neg);
 #pragma unroll
       for (int kk = 0; kk < BK / 8; ++kk) {
         // K-major: 8 floats = 32 bytes along the swizzled row; MN-major: 8 K-rows = 1024 bytes
-        const uint64_t ad = A_MN ? make_desc(sa + kk * 1024, BK * 128, 512, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
-        const uint64_t bd = B_MN ? make_desc(sb + kk * 1024, BK * 128, 512, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
-        umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t oa = A_MN ? kk * 1024 : kk * 32, ob = B_MN ? kk * 1024 : kk * 32;
+        auto adesc = [&](uint32_t base) { return A_MN ? make_desc(base + oa, BK * 128, 512, 1) : make_desc(base + oa, 16, 1024, 2); };
+        auto bdesc = [&](uint32_t base) { return B_MN ? make_desc(base + ob, BK * 128, 512, 1) : make_desc(base + ob, 16, 1024, 2); };
+        umma_tf32(tmem_base, adesc(sa), bdesc(sb), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        if (SPLIT) {
+          // x = trunc(x) + lo(x): the two cross terms restore the bits the tensor core drops
+          if (lo_mask & 1) umma_tf32(tmem_base, adesc(sa + LO_OFF), bdesc(sb), idesc, 1u);
+          if (lo_mask & 2) umma_tf32(tmem_base, adesc(sa), bdesc(sb + LO_OFF), idesc, 1u);
+        }
       }
       umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs have read it
     }
     umma_commit(tfull);                     // accumulator complete
   } else if (warp >= 2) {
-    // ===== epilogue: TMEM -> registers -> bias / activation / sampling -> global =====
+    if (SPLIT && twins) {
+      // ===== lo twins: x - trunc_tf32(x), element by element (the swizzle is the same on both sides) =====
+      const int te = threadIdx.x - 64;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, it = i / STAGES;
+        mbar_wait(full0 + 8 * s, it & 1);
+        float4* st = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (!(lo_mask & (1 << half))) continue;
+          const float4* src = st + half * (A_BYTES / 16);
+          float4* dst = st + (LO_OFF + half * A_BYTES) / 16;
+#pragma unroll
+          for (int r = 0; r < A_BYTES / 16 / NEPI; ++r) {
+            const float4 x = src[te + r * NEPI];
+            dst[te + r * NEPI] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the MMA's async-proxy reads
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8 * s) : "memory");
+      }
+    }
+    // ===== epilogue: TMEM -> registers -> bias / activation / sampling (or the W update) -> global =====
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;           // a warp may only touch its own 32 TMEM lanes
@@ -206,61 +325,47 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
       if (m < M && nkb > 0) {
         if (EPI == EPI_PART) {
           float* dst = ep.part + ((size_t)blockIdx.z * M + m) * N + nb;
+          if (ep.vec4 && nb + 32 <= N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) dst[j] = __uint_as_float(r[j]);
-        } else if (ep.vec4 && nb + 32 <= N) {
-          // 4 columns per step: one Philox block feeds 4 draws, 16-byte stores
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+          }
+        } else if (EPI == EPI_UPDATE) {
+          // rows of W are padded to ldw (a multiple of 4) with zeros that stay zero under the update (their
+          // statistics are the TMA's out-of-bounds zeros), so whole quads are processed up to ldw
+          float* wp = ep.uW + (size_t)m * ep.uldw + nb;
+          float* sp = ep.uS + (size_t)m * ep.uldw + nb;
+          const float* np = ep.uSnap ? ep.uSnap + (size_t)m * ep.uldw + nb : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int n = nb + j;
-            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n);
-            float pre[4] = {__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
-                            __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w};
-            float mu[4], x[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) mu[t] = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre[t]) : pre[t];
-            if (ep.pre) *reinterpret_cast<float4*>(ep.pre + m * ep.ld_pre + n) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-            if (ep.mean) *reinterpret_cast<float4*>(ep.mean + m * ep.ld_mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
-            if (ep.sample) {
-              const long long e = (long long)m * N + n;      // multiple of 4 on this path
-              if (ep.smp == SMP_BERNOULLI) {
-                float u[4];
-                if (ep.rs.mode == MDBN_RNG_BUFFER) {
-                  const float4 uv = __ldg(reinterpret_cast<const float4*>(ep.rs.seg + e));
-                  u[0] = uv.x; u[1] = uv.y; u[2] = uv.z; u[3] = uv.w;
-                } else {
-                  Philox4 ph = philox4x32_10((uint32_t)(e >> 2), ep.rs.c1, ep.rs.c2, ep.rs.c3, ep.rs.k0, ep.rs.k1);
-                  u[0] = u24(ph.x); u[1] = u24(ph.y); u[2] = u24(ph.z); u[3] = u24(ph.w);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) x[t] = u[t] < mu[t] ? 1.f : 0.f;
-              } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) x[t] = ep.smp == SMP_GAUSS ? mu[t] + rng_normal(ep.rs, e + t) : mu[t];
-              }
-              *reinterpret_cast<float4*>(ep.sample + m * ep.ld_sample + n) = make_float4(x[0], x[1], x[2], x[3]);
+            if (nb + j < ep.uldw) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wp + j), s4 = *reinterpret_cast<const float4*>(sp + j);
+              const float4 n4 = np ? *reinterpret_cast<const float4*>(np + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 wo, so;
+              update_one(ep.u, __uint_as_float(r[j]), w4.x, s4.x, n4.x, np != nullptr, wo.x, so.x);
+              update_one(ep.u, __uint_as_float(r[j + 1]), w4.y, s4.y, n4.y, np != nullptr, wo.y, so.y);
+              update_one(ep.u, __uint_as_float(r[j + 2]), w4.z, s4.z, n4.z, np != nullptr, wo.z, so.z);
+              update_one(ep.u, __uint_as_float(r[j + 3]), w4.w, s4.w, n4.w, np != nullptr, wo.w, so.w);
+              *reinterpret_cast<float4*>(wp + j) = wo;
+              *reinterpret_cast<float4*>(sp + j) = so;
             }
+          }
+        } else if (ep.vec4 && nb + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float a4[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3])};
+            epi_quad(ep, m, nb + j, N, a4);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < N) {
-              const float pre = __uint_as_float(r[j]) + ep.bias[n];
-              const float mu = ep.act == ACT_SIGMOID ? sigmoid_mufu(pre) : pre;
-              if (ep.pre) ep.pre[m * ep.ld_pre + n] = pre;
-              if (ep.mean) ep.mean[m * ep.ld_mean + n] = mu;
-              if (ep.sample) {
-                const long long e = (long long)m * N + n;
-                float x;
-                if (ep.smp == SMP_BERNOULLI) x = rng_uniform(ep.rs, e) < mu ? 1.f : 0.f;
-                else if (ep.smp == SMP_GAUSS) x = mu + rng_normal(ep.rs, e);
-                else x = mu;
-                ep.sample[m * ep.ld_sample + n] = x;
-              }
-            }
-          }
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < N) epi_one(ep, m, nb + j, N, __uint_as_float(r[j]));
         }
       }
     }
@@ -270,6 +375,32 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// split-K tail of propup / propdown: partial tiles summed in fixed order, then the same fused epilogue
+__global__ void part_act_kernel(const float* __restrict__ part, int splits, int M, int N, EpiParams ep) {
+  const long long total = (long long)M * N;
+  if (ep.vec4) {
+    const long long nq = total >> 2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+      const long long e = q << 2;
+      const int m = (int)(e / N), n = (int)(e - (long long)m * N);
+      float4 s = *reinterpret_cast<const float4*>(part + e);
+      for (int z = 1; z < splits; ++z) {
+        const float4 t = *reinterpret_cast<const float4*>(part + (size_t)z * total + e);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      const float a4[4] = {s.x, s.y, s.z, s.w};
+      epi_quad(ep, m, n, N, a4);
+    }
+  } else {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const int m = (int)(e / N), n = (int)(e - (long long)m * N);
+      float s = 0.f;
+      for (int z = 0; z < splits; ++z) s += part[(size_t)z * total + e];
+      epi_one(ep, m, n, N, s);
+    }
   }
 }
 
@@ -345,38 +476,66 @@ struct Operand {
   const float* ptr;
   long long ld;
   bool mn_major;      // true: memory is [K][MN]; false: memory is [MN][K]
+  bool exact;         // every value is exactly representable in TF32 ({0,1} samples): no lo twin in SPLIT mode
 };
 
-template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(mdbn_ctx* c, const Operand& A, const Operand& Bo, int M, int N, int K, int splits, int kneg,
-                       const EpiParams& ep, cudaStream_t st) {
+// split K over the SMs when the output has too few tiles to occupy them (skinny shapes); 1 = no split
+static int pick_splits(const mdbn_ctx* c, int M, int N, int K, bool split3) {
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN), nkb = (K + BK - 1) / BK;
+  const int slots = c->num_sms * (split3 ? 1 : 2);      // resident CTAs
+  if (2 * tiles > slots || nkb < 8) return 1;
+  int s = slots / tiles;
+  if (s > nkb / 4) s = nkb / 4;
+  return s < 1 ? 1 : s;
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT>
+static int launch_gemm_t(mdbn_ctx* c, const Operand& A, const Operand& Bo, int M, int N, int K, int splits, int kneg,
+                         const EpiParams& ep, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   if (A_MN) MDBN_TRY(make_map(&tmA, A.ptr, M, K, A.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmA, A.ptr, K, M, A.ld, BK, BM, false));
   if (B_MN) MDBN_TRY(make_map(&tmB, Bo.ptr, N, K, Bo.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmB, Bo.ptr, K, N, Bo.ld, BK, BN, false));
-  auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI>;
+  auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI, SPLIT>;
   static bool configured[64] = {};
   if (!configured[c->device]) {
-    MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MDBN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(SPLIT)));
     configured[c->device] = true;
   }
   const int nkb = (K + BK - 1) / BK;
   int kbps = (nkb + splits - 1) / splits;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (nkb + kbps - 1) / kbps);
-  kfn<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, M, N, K, kbps, kneg / BK, ep);
+  const int lo_mask = SPLIT ? ((A.exact ? 0 : 1) | (Bo.exact ? 0 : 2)) : 0;
+  kfn<<<grid, NTHREADS, smem_bytes(SPLIT), st>>>(tmA, tmB, M, N, K, kbps, kneg / BK, lo_mask, ep);
   c->launches++;
   MDBN_CUDA(cudaGetLastError());
   return 0;
 }
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(mdbn_ctx* c, bool split3, const Operand& A, const Operand& Bo, int M, int N, int K, int splits,
+                       int kneg, const EpiParams& ep, cudaStream_t st) {
+  return split3 ? launch_gemm_t<A_MN, B_MN, EPI, true>(c, A, Bo, M, N, K, splits, kneg, ep, st)
+                : launch_gemm_t<A_MN, B_MN, EPI, false>(c, A, Bo, M, N, K, splits, kneg, ep, st);
+}
+// number of K slices a launch with `splits` really has
+static int n_slices(int K, int splits) {
+  const int nkb = (K + BK - 1) / BK, kbps = (nkb + splits - 1) / splits;
+  return (nkb + kbps - 1) / kbps;
+}
 
 // ---- small ld-aware helpers of the tensor path ----------------------------------
+// rows b >= B of the batch tile (the statistics GEMM negates the nv/nh half per 32-row K block, so a minibatch that is
+// not a multiple of 32 is padded with zero rows) are written as zeros
 __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
-                                      int V, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
-  long long total = (long long)B * V;
+                                      int Bp, int V, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
+  long long total = (long long)Bp * V;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     int b = (int)(e / V), i = (int)(e % V);
-    long long r = idx ? idx[b] : b;
-    float x = data[r * ld + i];
+    float x = 0.f;
+    if (b < B) {
+      long long r = idx ? idx[b] : b;
+      x = data[r * ld + i];
+    }
     out[b * ldo + i] = x;
     if (xi) xi[b * ldo + i] = roundf(x);
   }
@@ -385,25 +544,38 @@ __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long 
 __global__ void gather_rows_ld4_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
                                        int V4, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
   const int b = blockIdx.y;
-  const long long r = idx ? idx[b] : b;
+  const bool real = b < B;
+  const long long r = real ? (idx ? idx[b] : b) : 0;
   const float4* src = reinterpret_cast<const float4*>(data + r * ld);
   float4* dst = reinterpret_cast<float4*>(out + (size_t)b * ldo);
   float4* dx = xi ? reinterpret_cast<float4*>(xi + (size_t)b * ldo) : nullptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V4; i += gridDim.x * blockDim.x) {
-    const float4 x = __ldg(src + i);
+    const float4 x = real ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     dst[i] = x;
     if (dx) dx[i] = make_float4(roundf(x.x), roundf(x.y), roundf(x.z), roundf(x.w));
   }
 }
-// raw column sums of (top half - bottom half) of a [2B, N] matrix, two deterministic stages:
-// row chunks in parallel, then a fixed-order sum of the chunk partials
-__global__ void col_diff_partial_kernel(const float* __restrict__ X, long long ld, int B, int N, int rows_per_chunk,
+// zero the padding rows [B, Bp) of the nv half of XV and of both halves of YH (scratch memory: a stale NaN times a
+// zero row of the other operand would poison the statistics)
+__global__ void zero_pad_rows_kernel(float* __restrict__ nv, long long ldx, int V, float* __restrict__ ph,
+                                     float* __restrict__ nh, long long ldy, int H, int npad) {
+  const long long nx = (long long)npad * ldx, ny = (long long)npad * ldy;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nx + 2 * ny;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e < nx) nv[e] = 0.f;
+    else if (e < nx + ny) ph[e - nx] = 0.f;
+    else nh[e - nx - ny] = 0.f;
+  }
+}
+// raw column sums of (top half - bottom half) of a [Bp + B, N] matrix (the bottom half starts at row Bp), two
+// deterministic stages: row chunks in parallel, then a fixed-order sum of the chunk partials
+__global__ void col_diff_partial_kernel(const float* __restrict__ X, long long ld, int B, int Bp, int N, int rows_per_chunk,
                                         float* __restrict__ partial) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
   float p = 0.f, q = 0.f;
-  for (int b = b0; b < b1; ++b) { p += X[(size_t)b * ld + n]; q += X[(size_t)(B + b) * ld + n]; }
+  for (int b = b0; b < b1; ++b) { p += X[(size_t)b * ld + n]; q += X[(size_t)(Bp + b) * ld + n]; }
   partial[(size_t)blockIdx.y * N + n] = p - q;
 }
 __global__ void col_diff_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
@@ -414,14 +586,42 @@ __global__ void col_diff_final_kernel(const float* __restrict__ partial, int chu
   s = warp_sum(s);
   if (lane == 0) out[n] = s;
 }
-static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int N, float* out, cudaStream_t st) {
+static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int Bp, int N, float* out, cudaStream_t st) {
   const int rpc = 32, chunks = (B + rpc - 1) / rpc;
   float* part = (float*)ws_get(c, WS_MISC, (size_t)chunks * N * sizeof(float));
   if (!part) return 3;
-  col_diff_partial_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, st>>>(X, ld, B, N, rpc, part);
+  col_diff_partial_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, st>>>(X, ld, B, Bp, N, rpc, part);
   col_diff_final_kernel<<<(N + 7) / 8, 256, 0, st>>>(part, chunks, N, out);
   c->launches += 2;
   return 0;
+}
+// Both bias gradients of a step with a moderate batch in ONE launch: column n < H is a hidden unit (rows of YH), the
+// rest are visible units (rows of XV); sum over the rows of (positive - negative), then either the raw sum goes to the
+// packed statistics (gsum != NULL) or the bias and its speed are updated in place (src/rbm.py:416-417, :361-364)
+__global__ void bias_tail_kernel(const float* __restrict__ YH, long long ldy, int H, const float* __restrict__ XV,
+                                 long long ldx, int V, int B, int Bp, const float* __restrict__ presum,
+                                 float* __restrict__ gsum, float* __restrict__ hb,
+                                 float* __restrict__ Shb, float* __restrict__ vb, float* __restrict__ Svb, float inv_rows,
+                                 float mom, float lr) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= H + V) return;
+  const bool hid = n < H;
+  const float* X = hid ? YH + n : XV + (n - H);
+  const long long ld = hid ? ldy : ldx;
+  float d;
+  if (presum) {
+    d = presum[n];          // (large batch: the sums were built by the two-stage column reduction)
+  } else {
+    float p = 0.f, q = 0.f;
+    for (int b = 0; b < B; ++b) { p += X[(size_t)b * ld]; q += X[(size_t)(Bp + b) * ld]; }
+    d = p - q;
+  }
+  if (gsum) { gsum[n] = d; return; }
+  float* bias = hid ? hb + n : vb + (n - H);
+  float* S = hid ? Shb + n : Svb + (n - H);
+  const float g = d * inv_rows, s = *S;
+  *S = g + (s - g) * mom;
+  *bias = *bias + s * lr;
 }
 __global__ void recon_cost_ld_kernel(const float* __restrict__ prev, const float* __restrict__ v0, long long ld, int B,
                                      int V, int kind, float* __restrict__ partial) {
@@ -459,22 +659,41 @@ __global__ void pl_row_ld_kernel(const float* __restrict__ prex, long long ldy, 
     partial[b] = -(float)V * softplusf_((h1 - h0) + vterm);
   }
 }
+// fixed-order sum of the cost partials; the packed statistics get (numerator, rows), a full step its cost
+// (numerator * inv_den); the pseudo-likelihood cursor advances here too (src/rbm.py:445)
 __global__ void sum_tree_kernel(const float* __restrict__ partial, int n, float* __restrict__ out, float rows,
-                                float* __restrict__ rows_out) {
+                                float* __restrict__ rows_out, float* __restrict__ cost_out, float inv_den,
+                                int* __restrict__ bit_idx, int V) {
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) { *out = s; *rows_out = rows; }
-}
-__global__ void bump_bit_kernel(int* bit_idx, int V) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *bit_idx = (*bit_idx + 1) % V;
+  if (threadIdx.x == 0) {
+    if (out) { *out = s; *rows_out = rows; }
+    if (cost_out) *cost_out = s * inv_den;
+    if (bit_idx) *bit_idx = (*bit_idx + 1) % V;
+  }
 }
 __global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + e];
     out[e] = s;
+  }
+}
+// split-K statistics of a full step: partials summed in fixed order and the update applied in the same pass
+__global__ void reduce_update_kernel(const float* __restrict__ part, int splits, int V, int H, float* __restrict__ W,
+                                     float* __restrict__ S, const float* __restrict__ Wsnap, int ldw, UpdateScalars u) {
+  const long long total = (long long)V * H;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / H), j = (int)(e - (long long)i * H);
+    float g = 0.f;
+    for (int z = 0; z < splits; ++z) g += part[(size_t)z * total + e];
+    const size_t o = (size_t)i * ldw + j;
+    float wo, so;
+    update_one(u, g, W[o], S[o], Wsnap ? Wsnap[o] : 0.f, Wsnap != nullptr, wo, so);
+    W[o] = wo;
+    S[o] = so;
   }
 }
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
@@ -492,25 +711,46 @@ static int vec_ok(const EpiParams& ep, int N) {
                 (ep.rs.mode == MDBN_RNG_BUFFER ? (uintptr_t)ep.rs.seg : 0);
   return N % 4 == 0 && ep.ld_pre % 4 == 0 && (a & 15) == 0;
 }
-static int up(mdbn_ctx* c, const float* W, int ldw, const float* hb, int B, int V, int H, const float* x, long long ldx,
-              float* pre, float* mean, float* sample, long long ldo, const RngSeg& rs, cudaStream_t st) {
+// one propagation: the GEMM with the fused epilogue, or — skinny shapes — split-K partials + the reduction kernel
+// that applies the same epilogue
+template <bool B_MN>
+static int propagate(mdbn_ctx* c, bool split3, const Operand& A, const Operand& Bo, int M, int N, int K, EpiParams ep,
+                     cudaStream_t st) {
+  ep.vec4 = vec_ok(ep, N);
+  const int splits = pick_splits(c, M, N, K, split3);
+  if (splits <= 1) return launch_gemm<false, B_MN, EPI_ACT>(c, split3, A, Bo, M, N, K, 1, 1 << 30, ep, st);
+  const int zs = n_slices(K, splits);
+  float* part = (float*)ws_get(c, WS_PART, (size_t)zs * M * N * sizeof(float));
+  if (!part) return 3;
+  EpiParams pp{};
+  pp.part = part;
+  pp.vec4 = N % 4 == 0;
+  MDBN_TRY((launch_gemm<false, B_MN, EPI_PART>(c, split3, A, Bo, M, N, K, splits, 1 << 30, pp, st)));
+  const long long work = ep.vec4 ? ((long long)M * N) >> 2 : (long long)M * N;
+  int blocks = (int)((work + 255) / 256);
+  if (blocks > 4 * c->num_sms) blocks = 4 * c->num_sms;
+  part_act_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(part, zs, M, N, ep);
+  c->launches++;
+  MDBN_CUDA(cudaGetLastError());
+  return 0;
+}
+static int up(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* hb, int B, int V, int H, const float* x,
+              long long ldx, bool x_exact, float* pre, float* mean, float* sample, long long ldo, const RngSeg& rs,
+              cudaStream_t st) {
   EpiParams ep{};
   ep.bias = hb; ep.act = ACT_SIGMOID; ep.smp = sample ? SMP_BERNOULLI : SMP_NONE; ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
-  ep.vec4 = vec_ok(ep, H);
-  return launch_gemm<false, true, EPI_ACT>(c, Operand{x, ldx, false}, Operand{W, ldw, true}, B, H, V, 1, 1 << 30, ep, st);
+  return propagate<true>(c, split3, Operand{x, ldx, false, x_exact}, Operand{W, ldw, true, false}, B, H, V, ep, st);
 }
-static int down(mdbn_ctx* c, const float* W, int ldw, const float* vb, int B, int V, int H, int kind, int noisy,
-                const float* h, long long ldh, float* pre, float* mean, float* sample, long long ldo, const RngSeg& rs,
-                cudaStream_t st) {
+static int down(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* vb, int B, int V, int H, int kind, int noisy,
+                const float* h, long long ldh, bool h_exact, float* pre, float* mean, float* sample, long long ldo,
+                const RngSeg& rs, cudaStream_t st) {
   EpiParams ep{};
   ep.bias = vb; ep.act = kind == MDBN_GRBM ? ACT_LINEAR : ACT_SIGMOID;
   ep.smp = !sample ? SMP_NONE : (kind == MDBN_GRBM ? (noisy ? SMP_GAUSS : SMP_MEAN) : SMP_BERNOULLI);
   ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
-  ep.vec4 = vec_ok(ep, V);
-  return launch_gemm<false, false, EPI_ACT>(c, Operand{h, ldh, false}, Operand{W, ldw, false}, B, V, H, 1, 1 << 30, ep,
-                                            st);
+  return propagate<false>(c, split3, Operand{h, ldh, false, h_exact}, Operand{W, ldw, false, false}, B, V, H, ep, st);
 }
 
 }  // namespace tc
@@ -518,18 +758,33 @@ static int down(mdbn_ctx* c, const float* W, int ldw, const float* vb, int B, in
 bool tensor_phase_supported(const void* W, int ldw, const void* x, long long ldx) {
   return ldw % 4 == 0 && ldx % 4 == 0 && (((uintptr_t)W | (uintptr_t)x) & 15) == 0 && tc::get_encode() != nullptr;
 }
+// single-phase calls: fp32-exact (SPLIT) unless the context allows plain TF32 (mdbn_set_tf32_phases)
 int tensor_propup(mdbn_ctx* c, const float* W, int ldw, const float* hb, const float* v, int ldv, int B, int V, int H,
                   float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st) {
-  return tc::up(c, W, ldw, hb, B, V, H, v, ldv, pre, mean, sample, H, rs, st);
+  return tc::up(c, !c->tf32_phases, W, ldw, hb, B, V, H, v, ldv, false, pre, mean, sample, H, rs, st);
 }
 int tensor_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
                     int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st) {
-  return tc::down(c, W, ldw, vb, B, V, H, kind, noisy, h, ldh, pre, mean, sample, V, rs, st);
+  return tc::down(c, !c->tf32_phases, W, ldw, vb, B, V, H, kind, noisy, h, ldh, false, pre, mean, sample, V, rs, st);
+}
+// F(v): the v W product on the tensor cores as split-K partials, softplus + row reduction in the tail kernel
+int tensor_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hb, const float* vb, const float* v, int ldv,
+                       int B, int V, int H, int kind, float* F, cudaStream_t st) {
+  using namespace tc;
+  const bool split3 = !c->tf32_phases;
+  const int splits = pick_splits(c, B, H, V, split3), zs = n_slices(V, splits);
+  float* part = (float*)ws_get(c, WS_PART, (size_t)zs * B * H * sizeof(float));
+  if (!part) return 3;
+  EpiParams pp{};
+  pp.part = part;
+  pp.vec4 = H % 4 == 0;
+  MDBN_TRY((launch_gemm<false, true, EPI_PART>(c, split3, Operand{v, ldv, false, false}, Operand{W, ldw, true, false}, B, H,
+                                               V, splits, 1 << 30, pp, st)));
+  return free_energy_from_parts(c, part, zs, B, H, hb, v, ldv, V, vb, kind, F, st);
 }
 
 bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a) {
-  if (a.B < 32 || a.B % tc::BK != 0) return false;          // the nv/nh half is negated per 32-row K block
-  if (a.ldw % 4 != 0 || ((uintptr_t)a.W & 15)) return false;
+  if (a.ldw % 4 != 0 || ((uintptr_t)a.W & 15) || ((uintptr_t)a.W_speed & 15) || ((uintptr_t)a.W_snap & 15)) return false;
   if (a.phase == MDBN_PHASE_APPLY) return false;
   return tc::get_encode() != nullptr;
 }
@@ -537,13 +792,15 @@ bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a) {
 int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   using namespace tc;
   const int B = a.B, V = a.V, H = a.H, k = a.k;
+  const int Bp = (B + BK - 1) / BK * BK;       // the nv/nh half of the statistics GEMM is negated per 32-row K block
+  const bool split3 = !a.tf32;                 // fp32-exact unless the caller allows plain TF32
+  const bool full = a.phase == MDBN_PHASE_FULL;
   const long long VH = (long long)V * H;
   const long long ldx = (V + 3) & ~3, ldy = (H + 3) & ~3;
-  float* G = a.phase == MDBN_PHASE_FULL ? (float*)ws_get(c, WS_G, (size_t)(VH + H + V + 2) * sizeof(float))
-                                        : a.stats_buf;
-  MDBN_CHECK(G != nullptr, "cd_step: stats buffer missing");
-  float* XV = (float*)ws_get(c, WS_XV, (size_t)2 * B * ldx * sizeof(float));
-  float* YH = (float*)ws_get(c, WS_YH, (size_t)2 * B * ldy * sizeof(float));
+  float* G = full ? nullptr : a.stats_buf;
+  MDBN_CHECK(full || G != nullptr, "cd_step: stats buffer missing");
+  float* XV = (float*)ws_get(c, WS_XV, (size_t)2 * Bp * ldx * sizeof(float));
+  float* YH = (float*)ws_get(c, WS_YH, (size_t)2 * Bp * ldy * sizeof(float));
   // PCD chain state: the caller's [B, H] array IS the chain buffer when its row stride suits TMA (H % 4 == 0, 16-byte
   // aligned): the Gibbs steps read and overwrite it in place, no copy in, no copy out (src/rbm.py:308-311, :369)
   const bool chain_in_place = a.persistent != nullptr && ldy == H && (((uintptr_t)a.persistent) & 15) == 0;
@@ -561,74 +818,114 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   }
   ULayout ul = u_layout(a.kind, a.noisy, B, V, H);
   const int eb = 4 * c->num_sms;
+  float* nv_mean = XV + (size_t)Bp * ldx;
+  float* nh_mean = YH + (size_t)Bp * ldy;
+  // v0 = data[indices] (+ round(v0) for the pseudo-likelihood); the padding rows of v0 are written as zeros
   if (V % 4 == 0 && a.ld_data % 4 == 0 && (((uintptr_t)a.data) & 15) == 0)
-    gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, B), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V / 4, XV, ldx, XI);
+    gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V / 4, XV,
+                                                                                    ldx, XI);
   else
-    gather_rows_ld_kernel<<<eb, 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V, XV, ldx, XI);
+    gather_rows_ld_kernel<<<eb, 256, 0, st>>>(a.data, a.ld_data, a.indices, B, pcd ? B : Bp, V, XV, ldx, XI);
   c->launches++;
+  if (Bp != B) {
+    if (pcd) MDBN_CUDA(cudaMemsetAsync(XV + (size_t)B * ldx, 0, (size_t)(Bp - B) * ldx * sizeof(float), st));   // (XI has B rows)
+    zero_pad_rows_kernel<<<64, 256, 0, st>>>(nv_mean + (size_t)B * ldx, ldx, V, YH + (size_t)B * ldy, nh_mean + (size_t)B * ldy,
+                                             ldy, H, Bp - B);
+    c->launches++;
+  }
   // positive phase
-  MDBN_TRY(up(c, a.W, a.ldw, a.hbias, B, V, H, XV, ldx, nullptr, YH, pcd ? nullptr : HS, ldy,
+  MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XV, ldx, false, nullptr, YH, pcd ? nullptr : HS, ldy,
               make_seg(a.rng, ul.off_h0, 0), st));
   if (pcd) {
-    MDBN_TRY(up(c, a.W, a.ldw, a.hbias, B, V, H, XI, ldx, PREX, nullptr, nullptr, ldy, make_seg(a.rng, 0, 0), st));
+    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XI, ldx, false, PREX, nullptr, nullptr, ldy, make_seg(a.rng, 0, 0),
+                st));
     if (!chain_in_place) {
       copy_rows_kernel<<<eb, 256, 0, st>>>(a.persistent, H, HS, ldy, B, H);      // chain state, padded stride for TMA
       c->launches++;
     }
   }
-  float* nv_mean = XV + (size_t)B * ldx;
-  float* nh_mean = YH + (size_t)B * ldy;
   for (int s = 0; s < k; ++s) {
     long long base = (long long)B * H + s * ul.step_stride;
-    MDBN_TRY(down(c, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldy, PREV, nv_mean,
+    // (the chain state is {0,1} once this step has sampled it; a caller-provided persistent chain is not assumed to be)
+    MDBN_TRY(down(c, split3, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldy, !(pcd && s == 0), PREV, nv_mean,
                   a.kind == MDBN_RBM ? VS : nullptr, ldx, make_seg(a.rng, base + ul.off_v, ord_v(s)), st));
     const float* v_in = a.kind == MDBN_GRBM ? nv_mean : VS;
-    MDBN_TRY(up(c, a.W, a.ldw, a.hbias, B, V, H, v_in, ldx, nullptr, nh_mean, HS, ldy,
+    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, v_in, ldx, a.kind == MDBN_RBM, nullptr, nh_mean, HS, ldy,
                 make_seg(a.rng, base + ul.off_h, ord_h(s)), st));
   }
-  // statistics: G = [v0;nv]^T (+/-) [ph;nh] over K = 2B, split-K across CTAs when V*H has few tiles
+  // monitoring cost on the OLD parameters (src/rbm.py:367-374), before anything is updated
+  {
+    float* num = full ? nullptr : G + VH + H + V;
+    const float den = (!pcd && a.kind == MDBN_GRBM) ? (float)B * (float)V : (float)B;      // :697 / :479-482
+    float* cost = full ? a.cost_out : nullptr;
+    if (pcd) {
+      pl_row_ld_kernel<<<B, 128, 0, st>>>(PREX, ldy, H, XI, ldx, V, a.W, a.ldw, a.vbias, a.bit_i_idx, a.kind, RED);
+      sum_tree_kernel<<<1, 256, 0, st>>>(RED, B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, a.bit_i_idx, V);
+      c->launches += 2;
+      if (!chain_in_place) {
+        copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldy, a.persistent, H, B, H);
+        c->launches++;
+      }
+    } else {
+      const int nb = 256;
+      recon_cost_ld_kernel<<<nb, 256, 0, st>>>(PREV, XV, ldx, B, V, a.kind, RED);
+      sum_tree_kernel<<<1, 256, 0, st>>>(RED, nb, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, nullptr, V);
+      c->launches += 2;
+    }
+  }
+  // statistics: [v0;nv]^T (+/-) [ph;nh] over K = 2 Bp.  A full step with enough output tiles applies the update in the
+  // GEMM's epilogue; few tiles (small layers, large batch) split K across the SMs and the update rides on the reduction
+  // of the partials.  STATS (data-parallel shard): the packed buffer gets the raw sums.
   {
     const int tiles = ((V + BM - 1) / BM) * ((H + BN - 1) / BN);
-    const int nkb = 2 * B / BK;
-    int splits = (2 * c->num_sms + tiles - 1) / tiles;
-    if (splits > nkb / 2) splits = nkb / 2 > 0 ? nkb / 2 : 1;
-    if (splits > 32) splits = 32;
-    if (splits < 1) splits = 1;
-    const int kbps = (nkb + splits - 1) / splits;
-    const int zs = (nkb + kbps - 1) / kbps;
-    float* part = (float*)ws_get(c, WS_PART, (size_t)zs * VH * sizeof(float));
-    if (!part) return 3;
-    EpiParams ep{};
-    ep.part = part;
-    MDBN_TRY((launch_gemm<true, true, EPI_PART>(c, Operand{XV, ldx, true}, Operand{YH, ldy, true}, V, H, 2 * B, splits, B,
-                                                ep, st)));
-    reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, VH, G);
-    c->launches++;
-    if (c->ev_stats_w) { MDBN_CUDA(cudaEventRecord(c->ev_stats_w, st)); c->ev_stats_w_done = true; }
+    const int nkb = 2 * Bp / BK;
+    const int slots = c->num_sms * (split3 ? 1 : 2);
+    int splits = 1;
+    if (2 * tiles <= slots) {
+      splits = (slots + tiles - 1) / tiles;
+      if (splits > nkb / 2) splits = nkb / 2 > 0 ? nkb / 2 : 1;
+      if (splits > 32) splits = 32;
+    }
+    const Operand Ao{XV, ldx, true, false}, Bo{YH, ldy, true, false};
+    const UpdateScalars u = make_update_scalars(a);
+    const float* snap = a.weightcost != 0.f ? a.W_snap : nullptr;
+    if (full && splits == 1) {
+      EpiParams ep{};
+      ep.uW = a.W; ep.uS = a.W_speed; ep.uSnap = snap; ep.uldw = a.ldw; ep.u = u;
+      MDBN_TRY((launch_gemm<true, true, EPI_UPDATE>(c, split3, Ao, Bo, V, H, 2 * Bp, 1, Bp, ep, st)));
+    } else {
+      const int zs = n_slices(2 * Bp, splits);
+      float* part = (float*)ws_get(c, WS_PART, (size_t)zs * VH * sizeof(float));
+      if (!part) return 3;
+      EpiParams ep{};
+      ep.part = part;
+      ep.vec4 = H % 4 == 0;
+      MDBN_TRY((launch_gemm<true, true, EPI_PART>(c, split3, Ao, Bo, V, H, 2 * Bp, splits, Bp, ep, st)));
+      if (full) reduce_update_kernel<<<eb, 256, 0, st>>>(part, zs, V, H, a.W, a.W_speed, snap, a.ldw, u);
+      else reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, VH, G);
+      c->launches++;
+      if (!full && c->ev_stats_w) { MDBN_CUDA(cudaEventRecord(c->ev_stats_w, st)); c->ev_stats_w_done = true; }
+    }
   }
-  MDBN_TRY(col_diff_sum(c, YH, ldy, B, H, G + VH, st));
-  MDBN_TRY(col_diff_sum(c, XV, ldx, B, V, G + VH + H, st));
-  if (pcd) {
-    pl_row_ld_kernel<<<B, 128, 0, st>>>(PREX, ldy, H, XI, ldx, V, a.W, a.ldw, a.vbias, a.bit_i_idx, a.kind, RED);
+  // bias gradients: raw sums into the packed buffer (STATS) or the in-place update (full step)
+  if (B <= 1024) {
+    bias_tail_kernel<<<(H + V + 255) / 256, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, nullptr, full ? nullptr : G + VH, a.hbias,
+                                                          a.hbias_speed, a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum,
+                                                          a.lr);
     c->launches++;
-    sum_tree_kernel<<<1, 256, 0, st>>>(RED, B, G + VH + H + V, (float)B, G + VH + H + V + 1);
-    c->launches++;
-    bump_bit_kernel<<<1, 32, 0, st>>>(a.bit_i_idx, V);
-    c->launches++;
-    if (!chain_in_place) {
-      copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldy, a.persistent, H, B, H);
+  } else {
+    float* gs = full ? (float*)ws_get(c, WS_G, (size_t)(H + V) * sizeof(float)) : G + VH;
+    if (!gs) return 3;
+    MDBN_TRY(col_diff_sum(c, YH, ldy, B, Bp, H, gs, st));
+    MDBN_TRY(col_diff_sum(c, XV, ldx, B, Bp, V, gs + H, st));
+    if (full) {
+      bias_tail_kernel<<<(H + V + 255) / 256, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, gs, nullptr, a.hbias, a.hbias_speed,
+                                                            a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum, a.lr);
       c->launches++;
     }
-  } else {
-    const int nb = 256;
-    recon_cost_ld_kernel<<<nb, 256, 0, st>>>(PREV, XV, ldx, B, V, a.kind, RED);
-    c->launches++;
-    sum_tree_kernel<<<1, 256, 0, st>>>(RED, nb, G + VH + H + V, (float)B, G + VH + H + V + 1);
-    c->launches++;
   }
   MDBN_CUDA(cudaGetLastError());
-  if (a.phase == MDBN_PHASE_STATS) return 0;
-  return apply_update(c, a, G, B, st);
+  return 0;
 }
 
 }  // namespace mdbn
