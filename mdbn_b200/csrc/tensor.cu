@@ -203,7 +203,7 @@ __device__ __forceinline__ void update_one(const UpdateScalars& u, float graw, f
 
 // lo_mask (SPLIT only): bit 0 = A has a lo twin (real-valued operand), bit 1 = B has one
 template <bool A_MN, bool B_MN, int EPI, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                                                            int kb_per_split, int kb_neg, int lo_mask, EpiParams ep) {
   constexpr int STAGE_BYTES = stage_bytes(SPLIT);
@@ -241,6 +241,18 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (EPI == EPI_UPDATE && warp == 0 && nkb > 0) {
+    // the W / W_speed (/ W_snap) tile this CTA will update: pull it into L2 while the mainloop runs
+    const int ncols = min(BN, ep.uldw - n0);
+    if (ncols > 0) {
+      for (int r = lane; r < BM && m0 + r < M; r += 32) {
+        const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
+        if (ep.uSnap) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uSnap + o), "r"(ncols * 4) : "memory");
+      }
+    }
+  }
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     for (int i = 0; i < nkb; ++i) {
@@ -311,61 +323,84 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8 * s) : "memory");
       }
     }
-    // ===== epilogue: TMEM -> registers -> bias / activation / sampling (or the W update) -> global =====
+    // ===== epilogue: TMEM -> registers -> (transposed through shared memory) -> bias / activation / sampling or
+    //       the W update -> global.  tcgen05.ld hands every thread one ROW of the tile; stored like that, a warp
+    //       instruction would touch 32 different cache lines.  Each warp therefore parks its 32 x 32 block in the
+    //       (now idle) stage memory and re-reads it as quads: 8 lanes cover one 128-byte row segment, a warp
+    //       instruction covers 4 complete lines — global loads and stores are coalesced. =====
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;           // a warp may only touch its own 32 TMEM lanes
     const int chalf = (warp - 2) >> 2;      // ... and the two warps of a quarter split the columns
-    const int m = m0 + quarter * 32 + lane;
+    constexpr int TLD = 36;                 // row stride of the parking tile (floats): 16-byte aligned, conflict-free
+    float* T = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * TLD);
+    const int trow = lane >> 3, tcol = 4 * (lane & 7);
 #pragma unroll 1
     for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
-      const int nb = n0 + c * 32;
-      if (m < M && nkb > 0) {
-        if (EPI == EPI_PART) {
-          float* dst = ep.part + ((size_t)blockIdx.z * M + m) * N + nb;
-          if (ep.vec4 && nb + 32 <= N) {
+      __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(T + lane * TLD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      __syncwarp();
+      const int n = n0 + c * 32 + tcol;
+      if (nkb <= 0) continue;
+      if (EPI == EPI_UPDATE) {
+        // rows of W are padded to ldw (a multiple of 4) with zeros that stay zero under the update (their
+        // statistics are the TMA's out-of-bounds zeros), so whole quads are processed up to ldw.  All loads of the
+        // eight row segments are issued before the first use: the tile comes from L2 at best, HBM at worst
+        if (n < ep.uldw) {
+          const bool hs = ep.uSnap != nullptr;
+          float4 w4[8], s4[8], n4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + quarter * 32 + 4 * i + trow;
+            const size_t o = (size_t)min(m, M - 1) * ep.uldw + n;
+            w4[i] = *reinterpret_cast<const float4*>(ep.uW + o);
+            s4[i] = *reinterpret_cast<const float4*>(ep.uS + o);
+            n4[i] = hs ? *reinterpret_cast<const float4*>(ep.uSnap + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + trow;
+            const int m = m0 + quarter * 32 + row;
+            if (m >= M) continue;
+            const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
+            float4 wo, so;
+            update_one(ep.u, a4v.x, w4[i].x, s4[i].x, n4[i].x, hs, wo.x, so.x);
+            update_one(ep.u, a4v.y, w4[i].y, s4[i].y, n4[i].y, hs, wo.y, so.y);
+            update_one(ep.u, a4v.z, w4[i].z, s4[i].z, n4[i].z, hs, wo.z, so.z);
+            update_one(ep.u, a4v.w, w4[i].w, s4[i].w, n4[i].w, hs, wo.w, so.w);
+            const size_t o = (size_t)m * ep.uldw + n;
+            *reinterpret_cast<float4*>(ep.uW + o) = wo;
+            *reinterpret_cast<float4*>(ep.uS + o) = so;
+          }
+        }
+        continue;
+      }
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + trow;
+        const int m = m0 + quarter * 32 + row;
+        if (m >= M) continue;
+        const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
+        const float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
+        if (EPI == EPI_PART) {
+          float* dst = ep.part + ((size_t)blockIdx.z * M + m) * N + n;
+          if (ep.vec4 && n + 4 <= N) {
+            *reinterpret_cast<float4*>(dst) = a4v;
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+            for (int t = 0; t < 4; ++t)
+              if (n + t < N) dst[t] = a4[t];
           }
-        } else if (EPI == EPI_UPDATE) {
-          // rows of W are padded to ldw (a multiple of 4) with zeros that stay zero under the update (their
-          // statistics are the TMA's out-of-bounds zeros), so whole quads are processed up to ldw
-          float* wp = ep.uW + (size_t)m * ep.uldw + nb;
-          float* sp = ep.uS + (size_t)m * ep.uldw + nb;
-          const float* np = ep.uSnap ? ep.uSnap + (size_t)m * ep.uldw + nb : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j < ep.uldw) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wp + j), s4 = *reinterpret_cast<const float4*>(sp + j);
-              const float4 n4 = np ? *reinterpret_cast<const float4*>(np + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 wo, so;
-              update_one(ep.u, __uint_as_float(r[j]), w4.x, s4.x, n4.x, np != nullptr, wo.x, so.x);
-              update_one(ep.u, __uint_as_float(r[j + 1]), w4.y, s4.y, n4.y, np != nullptr, wo.y, so.y);
-              update_one(ep.u, __uint_as_float(r[j + 2]), w4.z, s4.z, n4.z, np != nullptr, wo.z, so.z);
-              update_one(ep.u, __uint_as_float(r[j + 3]), w4.w, s4.w, n4.w, np != nullptr, wo.w, so.w);
-              *reinterpret_cast<float4*>(wp + j) = wo;
-              *reinterpret_cast<float4*>(sp + j) = so;
-            }
-          }
-        } else if (ep.vec4 && nb + 32 <= N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float a4[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3])};
-            epi_quad(ep, m, nb + j, N, a4);
-          }
+        } else if (ep.vec4 && n + 4 <= N) {
+          epi_quad(ep, m, n, N, a4);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) epi_one(ep, m, nb + j, N, __uint_as_float(r[j]));
+          for (int t = 0; t < 4; ++t)
+            if (n + t < N) epi_one(ep, m, n + t, N, a4[t]);
         }
       }
     }
@@ -526,18 +561,14 @@ static int n_slices(int K, int splits) {
 // rows b >= B of the batch tile (the statistics GEMM negates the nv/nh half per 32-row K block, so a minibatch that is
 // not a multiple of 32 is padded with zero rows) are written as zeros
 __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
-                                      int Bp, int V, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
-  long long total = (long long)Bp * V;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(e / V), i = (int)(e % V);
-    float x = 0.f;
-    if (b < B) {
-      long long r = idx ? idx[b] : b;
-      x = data[r * ld + i];
-    }
-    out[b * ldo + i] = x;
-    if (xi) xi[b * ldo + i] = roundf(x);
+                                      int V, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
+  const int b = blockIdx.y;      // rows b >= B are the zero padding
+  const bool real = b < B;
+  const float* src = data + (real ? (idx ? idx[b] : b) : 0) * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+    const float x = real ? __ldg(src + i) : 0.f;
+    out[(size_t)b * ldo + i] = x;
+    if (xi) xi[(size_t)b * ldo + i] = roundf(x);
   }
 }
 // the same, four columns per thread (V, strides and pointers multiples of 4 / 16 bytes): one row per blockIdx.y
@@ -597,24 +628,35 @@ static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int Bp
 }
 // Both bias gradients of a step with a moderate batch in ONE launch: column n < H is a hidden unit (rows of YH), the
 // rest are visible units (rows of XV); sum over the rows of (positive - negative), then either the raw sum goes to the
-// packed statistics (gsum != NULL) or the bias and its speed are updated in place (src/rbm.py:416-417, :361-364)
+// packed statistics (gsum != NULL) or the bias and its speed are updated in place (src/rbm.py:416-417, :361-364).
+// Block = 32 columns x 8 row groups (coalesced 128-byte reads, 8 loads in flight per column), combined in fixed order.
 __global__ void bias_tail_kernel(const float* __restrict__ YH, long long ldy, int H, const float* __restrict__ XV,
                                  long long ldx, int V, int B, int Bp, const float* __restrict__ presum,
                                  float* __restrict__ gsum, float* __restrict__ hb,
                                  float* __restrict__ Shb, float* __restrict__ vb, float* __restrict__ Svb, float inv_rows,
                                  float mom, float lr) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= H + V) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const bool ok = n < H + V;
   const bool hid = n < H;
-  const float* X = hid ? YH + n : XV + (n - H);
-  const long long ld = hid ? ldy : ldx;
-  float d;
+  float d = 0.f;
+  if (ok && !presum) {
+    const float* X = hid ? YH + n : XV + (n - H);
+    const long long ld = hid ? ldy : ldx;
+    float p = 0.f, q = 0.f;
+    for (int b = ty; b < B; b += 8) { p += X[(size_t)b * ld]; q += X[(size_t)(Bp + b) * ld]; }
+    d = p - q;
+  }
+  red[ty][tx] = d;
+  __syncthreads();
+  if (ty != 0 || !ok) return;
   if (presum) {
     d = presum[n];          // (large batch: the sums were built by the two-stage column reduction)
   } else {
-    float p = 0.f, q = 0.f;
-    for (int b = 0; b < B; ++b) { p += X[(size_t)b * ld]; q += X[(size_t)(Bp + b) * ld]; }
-    d = p - q;
+    d = red[0][tx];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) d += red[t][tx];
   }
   if (gsum) { gsum[n] = d; return; }
   float* bias = hid ? hb + n : vb + (n - H);
@@ -623,19 +665,22 @@ __global__ void bias_tail_kernel(const float* __restrict__ YH, long long ldy, in
   *S = g + (s - g) * mom;
   *bias = *bias + s * lr;
 }
+// reconstruction-cost numerators, one minibatch row per blockIdx.y (src/rbm.py:479-480 CE; :697 MSE with sigma of the
+// linear mean): partial[blockIdx.y * gridDim.x + blockIdx.x]
 __global__ void recon_cost_ld_kernel(const float* __restrict__ prev, const float* __restrict__ v0, long long ld, int B,
                                      int V, int kind, float* __restrict__ partial) {
   __shared__ float red[32];
   float s = 0.f;
-  long long n = (long long)B * V;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(e / V), i = (int)(e % V);
-    float p = prev[b * ld + i], t = v0[b * ld + i];
+  const int b = blockIdx.y;
+  const float* pr = prev + (size_t)b * ld;
+  const float* tr = v0 + (size_t)b * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+    const float p = pr[i], t = tr[i];
     if (kind == MDBN_GRBM) { float d = sigmoidf_(p) - t; s += d * d; }
     else s += t * softplusf_(-p) + (1.f - t) * softplusf_(p);
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 }
 __global__ void pl_row_ld_kernel(const float* __restrict__ prex, long long ldy, int H, const float* __restrict__ xi,
                                  long long ldx, int V, const float* __restrict__ W, int ldw, const float* __restrict__ vb,
@@ -825,7 +870,7 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V / 4, XV,
                                                                                     ldx, XI);
   else
-    gather_rows_ld_kernel<<<eb, 256, 0, st>>>(a.data, a.ld_data, a.indices, B, pcd ? B : Bp, V, XV, ldx, XI);
+    gather_rows_ld_kernel<<<dim3((V + 1023) / 1024, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V, XV, ldx, XI);
   c->launches++;
   if (Bp != B) {
     if (pcd) MDBN_CUDA(cudaMemsetAsync(XV + (size_t)B * ldx, 0, (size_t)(Bp - B) * ldx * sizeof(float), st));   // (XI has B rows)
@@ -847,7 +892,8 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   for (int s = 0; s < k; ++s) {
     long long base = (long long)B * H + s * ul.step_stride;
     // (the chain state is {0,1} once this step has sampled it; a caller-provided persistent chain is not assumed to be)
-    MDBN_TRY(down(c, split3, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldy, !(pcd && s == 0), PREV, nv_mean,
+    MDBN_TRY(down(c, split3, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldy, !(pcd && s == 0),
+                  a.kind == MDBN_GRBM ? nullptr : PREV, nv_mean,
                   a.kind == MDBN_RBM ? VS : nullptr, ldx, make_seg(a.rng, base + ul.off_v, ord_v(s)), st));
     const float* v_in = a.kind == MDBN_GRBM ? nv_mean : VS;
     MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, v_in, ldx, a.kind == MDBN_RBM, nullptr, nh_mean, HS, ldy,
@@ -867,9 +913,11 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
         c->launches++;
       }
     } else {
-      const int nb = 256;
-      recon_cost_ld_kernel<<<nb, 256, 0, st>>>(PREV, XV, ldx, B, V, a.kind, RED);
-      sum_tree_kernel<<<1, 256, 0, st>>>(RED, nb, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, nullptr, V);
+      // (the linear Gaussian mean IS the pre-activation: no separate array for it)
+      int nbx = (V + 1023) / 1024;
+      while ((long long)nbx * B > 4096) nbx = (nbx + 1) / 2;
+      recon_cost_ld_kernel<<<dim3(nbx, B), 256, 0, st>>>(a.kind == MDBN_GRBM ? nv_mean : PREV, XV, ldx, B, V, a.kind, RED);
+      sum_tree_kernel<<<1, 256, 0, st>>>(RED, nbx * B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, nullptr, V);
       c->launches += 2;
     }
   }
@@ -909,7 +957,7 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   }
   // bias gradients: raw sums into the packed buffer (STATS) or the in-place update (full step)
   if (B <= 1024) {
-    bias_tail_kernel<<<(H + V + 255) / 256, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, nullptr, full ? nullptr : G + VH, a.hbias,
+    bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, nullptr, full ? nullptr : G + VH, a.hbias,
                                                           a.hbias_speed, a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum,
                                                           a.lr);
     c->launches++;
@@ -919,7 +967,7 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     MDBN_TRY(col_diff_sum(c, YH, ldy, B, Bp, H, gs, st));
     MDBN_TRY(col_diff_sum(c, XV, ldx, B, Bp, V, gs + H, st));
     if (full) {
-      bias_tail_kernel<<<(H + V + 255) / 256, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, gs, nullptr, a.hbias, a.hbias_speed,
+      bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, gs, nullptr, a.hbias, a.hbias_speed,
                                                             a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum, a.lr);
       c->launches++;
     }
