@@ -43,6 +43,13 @@ WORKLOADS = {
                               l2=0.0, wc=0.0002),
     "mnist_rbm_pcd1_b20": dict(kind=0, V=784, H=500, B=20, k=1, pcd=True, N=49940, lr=0.1, mom=0.9, l1=0.0,
                                l2=0.0, wc=0.0002),
+    # batch 21..128 (north_star (c): "batch 10-100"): path=auto -> the tcgen05 path in fp32-exact split-TF32 arithmetic
+    "ge_grbm_pcd1_b32": dict(kind=1, V=19937, H=400, B=32, k=1, pcd=True, N=416, lr=0.005, mom=0.0, l1=0.01, l2=0.1, wc=0.0),
+    "ge_grbm_cd1_b50": dict(kind=1, V=19937, H=400, B=50, k=1, pcd=False, N=400, lr=0.005, mom=0.0, l1=0.01, l2=0.1, wc=0.0),
+    "ge_grbm_pcd1_b100": dict(kind=1, V=19937, H=400, B=100, k=1, pcd=True, N=400, lr=0.005, mom=0.0, l1=0.01, l2=0.1,
+                              wc=0.0),
+    "mnist_rbm_cd1_b100": dict(kind=0, V=784, H=500, B=100, k=1, pcd=False, N=50000, lr=0.1, mom=0.9, l1=0.0, l2=0.0,
+                               wc=0.0002),
     # BASELINE.json configs[4]: large-batch / many-chain PCD on the tcgen05 TF32 path; with --gpus N the
     # minibatch rows (and chains) are sharded over ranks and the packed statistics all-reduced (strong scaling)
     "rbm_784x500_b8192_pcd1_tf32": dict(kind=0, V=784, H=500, B=8192, k=1, pcd=True, N=65536, lr=0.1, mom=0.9,
@@ -510,7 +517,10 @@ def main():
                     "algorithmic_flops_per_step_per_gpu": aflops}
         else:
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_how": traffic_note, "kernel": "cd_skinny_kernel", "peak_source": how,
+                    "traffic": traffic, "traffic_how": traffic_note,
+                    "kernel": "cd_skinny_kernel" if B <= 20 else "tc_gemm_kernel<SPLIT> (tcgen05, fp32-exact split TF32; "
+                                                                 "statistics GEMM with the update fused in its epilogue)",
+                    "peak_source": how,
                     "algorithmic_bytes_per_step": abytes, "steps_per_launch": chain,
                     "algorithmic_bytes_per_launch": abytes * chain}
             if single:
@@ -522,7 +532,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if dp else "weak",
-            "vs_baseline": None, "dtype": "tf32" if tensor else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32" if tensor else ("f32" if B <= 20 else "f32 (3xTF32 on tcgen05)"), "data": "synthetic",
             "config": config_of(args.workload, w),
             "notes": {"rng": "philox4x32-10 in-kernel",
                       "launches": ("one launch per epoch of %d minibatches (TrainFn.run_steps -> mdbn_cd_steps), as "

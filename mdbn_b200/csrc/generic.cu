@@ -298,14 +298,10 @@ __global__ void update_w_kernel(float* __restrict__ W, float* __restrict__ S, co
        e += (long long)gridDim.x * blockDim.x) {
     int i = (int)(e / H), j = (int)(e % H);
     size_t o = (size_t)i * ldw + j;
-    float w = W[o], s = S[o];
-    float g = G[e] * u.inv_bnom;
-    if (Wsnap) g -= u.wc * Wsnap[o];
-    float D = 1.0f + u.c1 / (fabsf(w) + 0.001f);
-    g = g / D;
-    float mult = u.decay / D;
-    S[o] = g + (s - g) * u.mom;
-    W[o] = w * mult + s * u.lr;     // OLD speed: Theano updates are simultaneous (App. C-1)
+    float wo, so;      // (one formula for every multi-kernel path: the data-parallel APPLY equals the fused full step)
+    update_one(u, G[e], W[o], S[o], Wsnap ? Wsnap[o] : 0.f, Wsnap != nullptr, wo, so);
+    S[o] = so;
+    W[o] = wo;
   }
 }
 

@@ -41,10 +41,20 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
 constexpr int LO_OFF = A_BYTES + B_BYTES;      // SPLIT: the lo twins of A and B sit behind the pair
 __host__ __device__ constexpr int stage_bytes(bool split) { return (A_BYTES + B_BYTES) * (split ? 2 : 1); }
-__host__ __device__ constexpr int smem_bytes(bool split) { return STAGES * stage_bytes(split) + 1024 /*align*/ + 256 /*barriers*/; }
-constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter: column halves)
-constexpr int NEPI = NTHREADS - 64;
-constexpr int TMEM_COLS = 128;
+// Thread layout.  Plain mode: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter: column halves);
+// 2 CTAs per SM, one tile per CTA.  SPLIT mode: four more warps (2-5) build the lo twins, warps 6-13 are the epilogue;
+// one PERSISTENT CTA per SM walks the tiles with the accumulator double-buffered in TMEM, so the epilogue of a tile
+// (global loads and stores of the update) overlaps the mainloop of the next one.
+__host__ __device__ constexpr int n_threads(bool split) { return split ? 448 : 320; }
+__host__ __device__ constexpr int epi_warp0(bool split) { return split ? 6 : 2; }
+constexpr int N_XFORM = 128;                   // transform threads (SPLIT)
+constexpr int TLD = 20;                        // row stride (floats) of an epilogue warp's 32 x 16 parking tile
+constexpr int T_BYTES = 8 * 32 * TLD * 4;      // eight epilogue warps
+__host__ __device__ constexpr int tmem_cols(bool split) { return split ? 256 : 128; }
+__host__ __device__ constexpr int smem_bytes(bool split) {
+  // the plain mode parks the epilogue tiles in the (by then idle) stages; the persistent mode needs its own room
+  return STAGES * stage_bytes(split) + 1024 /*align*/ + 256 /*barriers*/ + (split ? T_BYTES : 0);
+}
 
 enum { EPI_ACT = 0, EPI_PART = 1, EPI_UPDATE = 2 };
 enum { ACT_SIGMOID = 0, ACT_LINEAR = 1 };
@@ -97,6 +107,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // shared-memory matrix descriptor (SM100 UMMA).  K-major tiles use the plain 128-byte swizzle (16-byte
 // chunks); MN-major TF32 operands only exist in the 128-byte swizzle with 32-byte atoms (4-row period).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -130,6 +146,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -186,53 +211,51 @@ __device__ __forceinline__ void epi_one(const EpiParams& ep, int m, int n, int N
     ep.sample[m * ep.ld_sample + n] = x;
   }
 }
-// W, W_speed update of one element from its raw statistic g = (v0^T ph - nv^T nh)[i][j]   src/rbm.py:347-365, :411-415
-__device__ __forceinline__ void update_one(const UpdateScalars& u, float graw, float w, float s, float snap, bool has_snap,
-                                           float& w_out, float& s_out) {
-  float g = graw * u.inv_bnom;
-  if (has_snap) g -= u.wc * snap;
-  float mult = u.decay;
-  if (u.c1 != 0.f) {
-    const float D = 1.0f + u.c1 / (fabsf(w) + 0.001f);
-    g = g / D;
-    mult = u.decay / D;
-  }
-  s_out = g + (s - g) * u.mom;
-  w_out = w * mult + s * u.lr;     // OLD speed: Theano updates are simultaneous (App. C-1)
-}
-
-// lo_mask (SPLIT only): bit 0 = A has a lo twin (real-valued operand), bit 1 = B has one
+// lo_mask (SPLIT only): bit 0 = A has a lo twin (real-valued operand), bit 1 = B has one.
+// Work items = (n tile, m tile, K slice), n fastest.  Plain mode: one item per CTA (3-D grid).  SPLIT mode: a 1-D grid
+// of persistent CTAs, item = blockIdx.x + i * gridDim.x; the smem ring and its mbarrier phases run on across items.
 template <bool A_MN, bool B_MN, int EPI, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                                                           int kb_per_split, int kb_neg, int lo_mask, EpiParams ep) {
+__global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                   int kb_per_split, int kb_neg, int lo_mask, int mn3d, int nbx, int nby, int nbz, EpiParams ep) {
   constexpr int STAGE_BYTES = stage_bytes(SPLIT);
+  constexpr int EW0 = epi_warp0(SPLIT);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), ready0 = smem_u32(bars + 2 * STAGES),
-                 tfull = smem_u32(bars + 3 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+                 tfull0 = smem_u32(bars + 3 * STAGES), tempty0 = smem_u32(bars + 3 * STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb_total = (K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(nkb_total, kb_begin + kb_per_split);
-  const int nkb = kb_end - kb_begin;
   const bool twins = SPLIT && lo_mask != 0;
+  const int n_items = nbx * nby * nbz;
+  const int item0 = SPLIT ? (int)blockIdx.x : (int)(blockIdx.x + nbx * (blockIdx.y + nby * blockIdx.z));
+  const int item_step = SPLIT ? (int)gridDim.x : n_items;
+  auto decode = [&](int item, int& m0, int& n0, int& bz, int& kb_begin, int& nkb) {
+    const int bx = item % nbx, r = item / nbx, by = r % nby;
+    bz = r / nby;
+    m0 = by * BM;
+    n0 = bx * BN;
+    kb_begin = bz * kb_per_split;
+    nkb = min(nkb_total, kb_begin + kb_per_split) - kb_begin;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
-      mbar_init(ready0 + 8 * s, NEPI / 32);      // one arrival per transform warp
+      mbar_init(ready0 + 8 * s, N_XFORM / 32);      // one arrival per transform warp
     }
-    mbar_init(tfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 8);                // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
+                 "r"(tmem_cols(SPLIT))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -241,166 +264,222 @@ __global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (EPI == EPI_UPDATE && warp == 0 && nkb > 0) {
-    // the W / W_speed (/ W_snap) tile this CTA will update: pull it into L2 while the mainloop runs
-    const int ncols = min(BN, ep.uldw - n0);
-    if (ncols > 0) {
-      for (int r = lane; r < BM && m0 + r < M; r += 32) {
-        const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
-        if (ep.uSnap) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uSnap + o), "r"(ncols * 4) : "memory");
-      }
-    }
-  }
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES, it = i / STAGES;
-      mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
-      const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-      const uint32_t bar = full0 + 8 * s;
-      mbar_expect_tx(bar, A_BYTES + B_BYTES);
-      const int k0 = (kb_begin + i) * BK;
-      if (A_MN) {
-#pragma unroll
-        for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, bar, m0 + 32 * c, k0);
-      } else {
-        tma_load_2d(sa, &tmA, bar, k0, m0);
-      }
-      if (B_MN) {
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, bar, n0 + 32 * c, k0);
-      } else {
-        tma_load_2d(sb, &tmB, bar, k0, n0);
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES, it = i / STAGES;
-      mbar_wait((twins ? ready0 : full0) + 8 * s, it & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-      const uint32_t idesc = make_idesc(A_MN, B_MN, (kb_begin + i) >= kb_neg);
-#pragma unroll
-      for (int kk = 0; kk < BK / 8; ++kk) {
-        // K-major: 8 floats = 32 bytes along the swizzled row; MN-major: 8 K-rows = 1024 bytes
-        const uint32_t oa = A_MN ? kk * 1024 : kk * 32, ob = B_MN ? kk * 1024 : kk * 32;
-        auto adesc = [&](uint32_t base) { return A_MN ? make_desc(base + oa, BK * 128, 512, 1) : make_desc(base + oa, 16, 1024, 2); };
-        auto bdesc = [&](uint32_t base) { return B_MN ? make_desc(base + ob, BK * 128, 512, 1) : make_desc(base + ob, 16, 1024, 2); };
-        umma_tf32(tmem_base, adesc(sa), bdesc(sb), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-        if (SPLIT) {
-          // x = trunc(x) + lo(x): the two cross terms restore the bits the tensor core drops
-          if (lo_mask & 1) umma_tf32(tmem_base, adesc(sa + LO_OFF), bdesc(sb), idesc, 1u);
-          if (lo_mask & 2) umma_tf32(tmem_base, adesc(sa), bdesc(sb + LO_OFF), idesc, 1u);
-        }
-      }
-      umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs have read it
-    }
-    umma_commit(tfull);                     // accumulator complete
-  } else if (warp >= 2) {
-    if (SPLIT && twins) {
-      // ===== lo twins: x - trunc_tf32(x), element by element (the swizzle is the same on both sides) =====
-      const int te = threadIdx.x - 64;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, it = i / STAGES;
-        mbar_wait(full0 + 8 * s, it & 1);
-        float4* st = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (!(lo_mask & (1 << half))) continue;
-          const float4* src = st + half * (A_BYTES / 16);
-          float4* dst = st + (LO_OFF + half * A_BYTES) / 16;
-#pragma unroll
-          for (int r = 0; r < A_BYTES / 16 / NEPI; ++r) {
-            const float4 x = src[te + r * NEPI];
-            dst[te + r * NEPI] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+  if (warp == 0) {
+    // ===== TMA producer (lane 0); the whole warp first asks L2 for the W / W_speed tile of an update item =====
+    int g = 0;      // k-blocks issued so far: ring position and phase
+    for (int item = item0; item < n_items; item += item_step) {
+      int m0, n0, bz, kb_begin, nkb;
+      decode(item, m0, n0, bz, kb_begin, nkb);
+      if (EPI == EPI_UPDATE) {
+        const int ncols = min(BN, ep.uldw - n0);
+        if (ncols > 0) {
+          for (int r = lane; r < BM && m0 + r < M; r += 32) {
+            const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
+            if (ep.uSnap) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uSnap + o), "r"(ncols * 4) : "memory");
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the MMA's async-proxy reads
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8 * s) : "memory");
+      }
+      if (lane == 0) {
+        for (int i = 0; i < nkb; ++i, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint32_t bar = full0 + 8 * s;
+          mbar_expect_tx(bar, A_BYTES + B_BYTES);
+          const int k0 = (kb_begin + i) * BK;
+          if (A_MN) {
+            // MN-major tile = BM/32 chunks of {32 columns x BK rows}: one 3-D box when the operand is library scratch
+            // (view [chunk][k][32]; a ragged last chunk wraps into the next row: rows m >= M, discarded), else a box
+            // per chunk
+            if (mn3d & 1) {
+              tma_load_3d(sa, &tmA, bar, 0, k0, m0 >> 5);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, bar, m0 + 32 * c, k0);
+            }
+          } else {
+            tma_load_2d(sa, &tmA, bar, k0, m0);
+          }
+          if (B_MN) {
+            if (mn3d & 2) {
+              tma_load_3d(sb, &tmB, bar, 0, k0, n0 >> 5);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, bar, n0 + 32 * c, k0);
+            }
+          } else {
+            tma_load_2d(sb, &tmB, bar, k0, n0);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int g = 0, t = 0;
+      for (int item = item0; item < n_items; item += item_step, ++t) {
+        int m0, n0, bz, kb_begin, nkb;
+        decode(item, m0, n0, bz, kb_begin, nkb);
+        const int ab = SPLIT ? (t & 1) : 0;
+        const uint32_t tacc = tmem_base + ab * BN;
+        if (SPLIT) {
+          mbar_wait(tempty0 + 8 * ab, ((t >> 1) & 1) ^ 1);        // the epilogue has drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int i = 0; i < nkb; ++i, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          mbar_wait((twins ? ready0 : full0) + 8 * s, it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint32_t idesc = make_idesc(A_MN, B_MN, (kb_begin + i) >= kb_neg);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            // K-major: 8 floats = 32 bytes along the swizzled row; MN-major: 8 K-rows = 1024 bytes
+            const uint32_t oa = A_MN ? kk * 1024 : kk * 32, ob = B_MN ? kk * 1024 : kk * 32;
+            auto adesc = [&](uint32_t base) { return A_MN ? make_desc(base + oa, BK * 128, 512, 1) : make_desc(base + oa, 16, 1024, 2); };
+            auto bdesc = [&](uint32_t base) { return B_MN ? make_desc(base + ob, BK * 128, 512, 1) : make_desc(base + ob, 16, 1024, 2); };
+            umma_tf32(tacc, adesc(sa), bdesc(sb), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            if (SPLIT) {
+              // x = trunc(x) + lo(x): the two cross terms restore the bits the tensor core drops
+              if (lo_mask & 1) umma_tf32(tacc, adesc(sa + LO_OFF), bdesc(sb), idesc, 1u);
+              if (lo_mask & 2) umma_tf32(tacc, adesc(sa), bdesc(sb + LO_OFF), idesc, 1u);
+            }
+          }
+          umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(tfull0 + 8 * ab);           // accumulator complete
       }
     }
+  } else if (SPLIT && warp < EW0) {
+    // ===== lo twins: x - trunc_tf32(x), element by element (the swizzle is the same on both sides) =====
+    if (twins) {
+      const int te = threadIdx.x - 64;
+      int g = 0;
+      for (int item = item0; item < n_items; item += item_step) {
+        int m0, n0, bz, kb_begin, nkb;
+        decode(item, m0, n0, bz, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          mbar_wait(full0 + 8 * s, it & 1);
+          float4* st = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (!(lo_mask & (1 << half))) continue;
+            const float4* src = st + half * (A_BYTES / 16);
+            float4* dst = st + (LO_OFF + half * A_BYTES) / 16;
+#pragma unroll
+            for (int r = 0; r < A_BYTES / 16 / N_XFORM; ++r) {
+              const float4 x = src[te + r * N_XFORM];
+              dst[te + r * N_XFORM] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the MMA's async-proxy reads
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8 * s) : "memory");
+        }
+      }
+    }
+  } else {
     // ===== epilogue: TMEM -> registers -> (transposed through shared memory) -> bias / activation / sampling or
     //       the W update -> global.  tcgen05.ld hands every thread one ROW of the tile; stored like that, a warp
-    //       instruction would touch 32 different cache lines.  Each warp therefore parks its 32 x 32 block in the
-    //       (now idle) stage memory and re-reads it as quads: 8 lanes cover one 128-byte row segment, a warp
-    //       instruction covers 4 complete lines — global loads and stores are coalesced. =====
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    //       instruction would touch 32 different cache lines.  Each warp therefore parks 32 rows x 16 columns in
+    //       shared memory and re-reads them as quads: 4 lanes cover a 64-byte row segment, a warp instruction covers 8
+    //       rows — whole sectors, coalesced. =====
+    const int ew = warp - EW0;
     const int quarter = warp & 3;           // a warp may only touch its own 32 TMEM lanes
-    const int chalf = (warp - 2) >> 2;      // ... and the two warps of a quarter split the columns
-    constexpr int TLD = 36;                 // row stride of the parking tile (floats): 16-byte aligned, conflict-free
-    float* T = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * TLD);
-    const int trow = lane >> 3, tcol = 4 * (lane & 7);
+    const int chalf = ew >> 2;              // ... and the two warps of a quarter split the columns
+    float* T = reinterpret_cast<float*>(SPLIT ? smem + STAGES * STAGE_BYTES + 256 : smem) + ew * (32 * TLD);
+    const int trow = lane >> 2, tcol = 4 * (lane & 3);
+    int t = 0;
+    for (int item = item0; item < n_items; item += item_step, ++t) {
+      int m0, n0, bz, kb_begin, nkb;
+      decode(item, m0, n0, bz, kb_begin, nkb);
+      const int ab = SPLIT ? (t & 1) : 0;
+      mbar_wait(tfull0 + 8 * ab, SPLIT ? ((t >> 1) & 1) : 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-    for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(T + lane * TLD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-      __syncwarp();
-      const int n = n0 + c * 32 + tcol;
-      if (nkb <= 0) continue;
-      if (EPI == EPI_UPDATE) {
-        // rows of W are padded to ldw (a multiple of 4) with zeros that stay zero under the update (their
-        // statistics are the TMA's out-of-bounds zeros), so whole quads are processed up to ldw.  All loads of the
-        // eight row segments are issued before the first use: the tile comes from L2 at best, HBM at worst
-        if (n < ep.uldw) {
-          const bool hs = ep.uSnap != nullptr;
-          float4 w4[8], s4[8], n4[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = m0 + quarter * 32 + 4 * i + trow;
-            const size_t o = (size_t)min(m, M - 1) * ep.uldw + n;
-            w4[i] = *reinterpret_cast<const float4*>(ep.uW + o);
-            s4[i] = *reinterpret_cast<const float4*>(ep.uS + o);
-            n4[i] = hs ? *reinterpret_cast<const float4*>(ep.uSnap + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + trow;
-            const int m = m0 + quarter * 32 + row;
-            if (m >= M) continue;
-            const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
-            float4 wo, so;
-            update_one(ep.u, a4v.x, w4[i].x, s4[i].x, n4[i].x, hs, wo.x, so.x);
-            update_one(ep.u, a4v.y, w4[i].y, s4[i].y, n4[i].y, hs, wo.y, so.y);
-            update_one(ep.u, a4v.z, w4[i].z, s4[i].z, n4[i].z, hs, wo.z, so.z);
-            update_one(ep.u, a4v.w, w4[i].w, s4[i].w, n4[i].w, hs, wo.w, so.w);
-            const size_t o = (size_t)m * ep.uldw + n;
-            *reinterpret_cast<float4*>(ep.uW + o) = wo;
-            *reinterpret_cast<float4*>(ep.uS + o) = so;
-          }
+      for (int c = chalf * (BN / 32); c < (chalf + 1) * (BN / 32); ++c) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * BN + c * 16, r);
+        if (SPLIT && c == (chalf + 1) * (BN / 32) - 1) {
+          // last read of this accumulator by this warp: hand it back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * ab) : "memory");
         }
-        continue;
-      }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(T + lane * TLD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        const int n = n0 + c * 16 + tcol;
+        if (nkb <= 0) continue;
+        if (EPI == EPI_UPDATE) {
+          // The loads of all row segments are issued before the first use (the tile comes from L2 at best, HBM at
+          // worst).  Padding columns n >= N of W (zeros) are left alone: with a 3-D operand box their statistics are
+          // not the TMA's out-of-bounds zeros.
+          if (n < N) {
+            const bool hs = ep.uSnap != nullptr, whole = n + 4 <= N;
+            float4 w4[4], s4[4], n4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + quarter * 32 + 8 * i + trow;
+              const size_t o = (size_t)min(m, M - 1) * ep.uldw + n;
+              w4[i] = *reinterpret_cast<const float4*>(ep.uW + o);
+              s4[i] = *reinterpret_cast<const float4*>(ep.uS + o);
+              n4[i] = hs ? *reinterpret_cast<const float4*>(ep.uSnap + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + trow;
+              const int m = m0 + quarter * 32 + row;
+              if (m >= M) continue;
+              const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
+              float4 wo, so;
+              update_one(ep.u, a4v.x, w4[i].x, s4[i].x, n4[i].x, hs, wo.x, so.x);
+              update_one(ep.u, a4v.y, w4[i].y, s4[i].y, n4[i].y, hs, wo.y, so.y);
+              update_one(ep.u, a4v.z, w4[i].z, s4[i].z, n4[i].z, hs, wo.z, so.z);
+              update_one(ep.u, a4v.w, w4[i].w, s4[i].w, n4[i].w, hs, wo.w, so.w);
+              const size_t o = (size_t)m * ep.uldw + n;
+              if (whole) {
+                *reinterpret_cast<float4*>(ep.uW + o) = wo;
+                *reinterpret_cast<float4*>(ep.uS + o) = so;
+              } else {
+                const float wf[4] = {wo.x, wo.y, wo.z, wo.w}, sf[4] = {so.x, so.y, so.z, so.w};
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt)
+                  if (n + tt < N) { ep.uW[o + tt] = wf[tt]; ep.uS[o + tt] = sf[tt]; }
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll 2
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + trow;
-        const int m = m0 + quarter * 32 + row;
-        if (m >= M) continue;
-        const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
-        const float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
-        if (EPI == EPI_PART) {
-          float* dst = ep.part + ((size_t)blockIdx.z * M + m) * N + n;
-          if (ep.vec4 && n + 4 <= N) {
-            *reinterpret_cast<float4*>(dst) = a4v;
+        for (int i = 0; i < 4; ++i) {
+          const int row = 8 * i + trow;
+          const int m = m0 + quarter * 32 + row;
+          if (m >= M) continue;
+          const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
+          const float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
+          if (EPI == EPI_PART) {
+            float* dst = ep.part + ((size_t)bz * M + m) * N + n;
+            if (ep.vec4 && n + 4 <= N) {
+              *reinterpret_cast<float4*>(dst) = a4v;
+            } else {
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt)
+                if (n + tt < N) dst[tt] = a4[tt];
+            }
+          } else if (ep.vec4 && n + 4 <= N) {
+            epi_quad(ep, m, n, N, a4);
           } else {
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (n + t < N) dst[t] = a4[t];
+            for (int tt = 0; tt < 4; ++tt)
+              if (n + tt < N) epi_one(ep, m, n + tt, N, a4[tt]);
           }
-        } else if (ep.vec4 && n + 4 <= N) {
-          epi_quad(ep, m, n, N, a4);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (n + t < N) epi_one(ep, m, n + t, N, a4[t]);
         }
       }
     }
@@ -409,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(SPLIT)) : "memory");
   }
 }
 
@@ -512,7 +591,33 @@ struct Operand {
   long long ld;
   bool mn_major;      // true: memory is [K][MN]; false: memory is [MN][K]
   bool exact;         // every value is exactly representable in TF32 ({0,1} samples): no lo twin in SPLIT mode
+  bool scratch3d;     // MN-major library scratch (slack behind the last row): whole-tile 3-D TMA boxes
 };
+// MN-major operand [K][MN] viewed as [chunk = MN/32][k][32]: ONE box {32, BK, tile/32} per k-block lands in shared
+// memory exactly like the per-chunk 2-D boxes (chunk-major, 128-byte rows, 32-byte-atom swizzle).  The last chunk of a
+// ragged MN reads on into the next row (columns the epilogue discards) and, on the last row, up to 124 bytes past the
+// matrix — only for scratch buffers, which have that slack.
+static int make_map3(CUtensorMap* tm, const float* ptr, long long mn, long long k, long long ld, int tile) {
+  static thread_local MapCache cache;
+  const MapKey kq{ptr, mn, k, ld, tile, -3, 1};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == kq) { *tm = cache.map[i]; return 0; }
+  EncodeFn enc = get_encode();
+  MDBN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  MDBN_CHECK(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, "TMA operand must be 16-byte aligned (ptr %p ld %lld)",
+             (const void*)ptr, ld);
+  cuuint64_t dims[3] = {32, (cuuint64_t)k, (cuuint64_t)((mn + 31) / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)(tile / 32)};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MDBN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with %d", (int)r);
+  const int slot = cache.used < MapCache::N ? cache.used++ : (cache.next++ % MapCache::N);
+  cache.key[slot] = kq;
+  cache.map[slot] = *tm;
+  return 0;
+}
 
 // split K over the SMs when the output has too few tiles to occupy them (skinny shapes); 1 = no split
 static int pick_splits(const mdbn_ctx* c, int M, int N, int K, bool split3) {
@@ -528,8 +633,13 @@ template <bool A_MN, bool B_MN, int EPI, bool SPLIT>
 static int launch_gemm_t(mdbn_ctx* c, const Operand& A, const Operand& Bo, int M, int N, int K, int splits, int kneg,
                          const EpiParams& ep, cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  if (A_MN) MDBN_TRY(make_map(&tmA, A.ptr, M, K, A.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmA, A.ptr, K, M, A.ld, BK, BM, false));
-  if (B_MN) MDBN_TRY(make_map(&tmB, Bo.ptr, N, K, Bo.ld, 32, BK, true)); else MDBN_TRY(make_map(&tmB, Bo.ptr, K, N, Bo.ld, BK, BN, false));
+  const int mn3d = ((A_MN && A.scratch3d) ? 1 : 0) | ((B_MN && Bo.scratch3d) ? 2 : 0);
+  if (mn3d & 1) MDBN_TRY(make_map3(&tmA, A.ptr, M, K, A.ld, BM));
+  else if (A_MN) MDBN_TRY(make_map(&tmA, A.ptr, M, K, A.ld, 32, BK, true));
+  else MDBN_TRY(make_map(&tmA, A.ptr, K, M, A.ld, BK, BM, false));
+  if (mn3d & 2) MDBN_TRY(make_map3(&tmB, Bo.ptr, N, K, Bo.ld, BN));
+  else if (B_MN) MDBN_TRY(make_map(&tmB, Bo.ptr, N, K, Bo.ld, 32, BK, true));
+  else MDBN_TRY(make_map(&tmB, Bo.ptr, K, N, Bo.ld, BK, BN, false));
   auto kfn = tc_gemm_kernel<A_MN, B_MN, EPI, SPLIT>;
   static bool configured[64] = {};
   if (!configured[c->device]) {
@@ -538,9 +648,11 @@ static int launch_gemm_t(mdbn_ctx* c, const Operand& A, const Operand& Bo, int M
   }
   const int nkb = (K + BK - 1) / BK;
   int kbps = (nkb + splits - 1) / splits;
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (nkb + kbps - 1) / kbps);
+  const int nbx = (N + BN - 1) / BN, nby = (M + BM - 1) / BM, nbz = (nkb + kbps - 1) / kbps;
   const int lo_mask = SPLIT ? ((A.exact ? 0 : 1) | (Bo.exact ? 0 : 2)) : 0;
-  kfn<<<grid, NTHREADS, smem_bytes(SPLIT), st>>>(tmA, tmB, M, N, K, kbps, kneg / BK, lo_mask, ep);
+  // SPLIT: persistent CTAs, one per SM, walking the work items; plain: one CTA per item, two resident per SM
+  const dim3 grid = SPLIT ? dim3(nbx * nby * nbz < c->num_sms ? nbx * nby * nbz : c->num_sms) : dim3(nbx, nby, nbz);
+  kfn<<<grid, n_threads(SPLIT), smem_bytes(SPLIT), st>>>(tmA, tmB, M, N, K, kbps, kneg / BK, lo_mask, mn3d, nbx, nby, nbz, ep);
   c->launches++;
   MDBN_CUDA(cudaGetLastError());
   return 0;
@@ -785,7 +897,7 @@ static int up(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* hb
   EpiParams ep{};
   ep.bias = hb; ep.act = ACT_SIGMOID; ep.smp = sample ? SMP_BERNOULLI : SMP_NONE; ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
-  return propagate<true>(c, split3, Operand{x, ldx, false, x_exact}, Operand{W, ldw, true, false}, B, H, V, ep, st);
+  return propagate<true>(c, split3, Operand{x, ldx, false, x_exact, false}, Operand{W, ldw, true, false, false}, B, H, V, ep, st);
 }
 static int down(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* vb, int B, int V, int H, int kind, int noisy,
                 const float* h, long long ldh, bool h_exact, float* pre, float* mean, float* sample, long long ldo,
@@ -795,7 +907,7 @@ static int down(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* 
   ep.smp = !sample ? SMP_NONE : (kind == MDBN_GRBM ? (noisy ? SMP_GAUSS : SMP_MEAN) : SMP_BERNOULLI);
   ep.rs = rs;
   ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
-  return propagate<false>(c, split3, Operand{h, ldh, false, h_exact}, Operand{W, ldw, false, false}, B, V, H, ep, st);
+  return propagate<false>(c, split3, Operand{h, ldh, false, h_exact, false}, Operand{W, ldw, false, false, false}, B, V, H, ep, st);
 }
 
 }  // namespace tc
@@ -823,7 +935,7 @@ int tensor_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hb, co
   EpiParams pp{};
   pp.part = part;
   pp.vec4 = H % 4 == 0;
-  MDBN_TRY((launch_gemm<false, true, EPI_PART>(c, split3, Operand{v, ldv, false, false}, Operand{W, ldw, true, false}, B, H,
+  MDBN_TRY((launch_gemm<false, true, EPI_PART>(c, split3, Operand{v, ldv, false, false, false}, Operand{W, ldw, true, false, false}, B, H,
                                                V, splits, 1 << 30, pp, st)));
   return free_energy_from_parts(c, part, zs, B, H, hb, v, ldv, V, vb, kind, F, st);
 }
@@ -934,7 +1046,7 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
       if (splits > nkb / 2) splits = nkb / 2 > 0 ? nkb / 2 : 1;
       if (splits > 32) splits = 32;
     }
-    const Operand Ao{XV, ldx, true, false}, Bo{YH, ldy, true, false};
+    const Operand Ao{XV, ldx, true, false, true}, Bo{YH, ldy, true, false, true};
     const UpdateScalars u = make_update_scalars(a);
     const float* snap = a.weightcost != 0.f ? a.W_snap : nullptr;
     if (full && splits == 1) {
