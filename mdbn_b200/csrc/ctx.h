@@ -119,23 +119,25 @@ inline UpdateScalars make_update_scalars(const mdbn_cd_args& a) {
 
 // W, W_speed update of one element from its raw statistic g = (v0^T ph - nv^T nh)[i][j]   src/rbm.py:347-365, :411-415
 #ifdef __CUDACC__
+// (explicit rounding intrinsics: no context-dependent FMA contraction, so the fused epilogue, the reduction kernel and the
+//  data-parallel APPLY kernel produce the same bits from the same statistics)
 __device__ __forceinline__ void update_one(const UpdateScalars& u, float graw, float w, float s, float snap, bool has_snap,
                                            float& w_out, float& s_out) {
-  float g = graw * u.inv_bnom;
-  if (has_snap) g -= u.wc * snap;
+  float g = __fmul_rn(graw, u.inv_bnom);
+  if (has_snap) g = __fmaf_rn(-u.wc, snap, g);
   float mult = u.decay;
   if (u.c1 != 0.f) {
     // 1/D, D = 1 + 2 lr lambda_1 / (|W| + eps)  ==  (|W| + eps) / (|W| + eps + 2 lr lambda_1): ONE MUFU reciprocal
-    // (~1 ulp) instead of three IEEE divisions (they were 30 % of this kernel's instructions)      src/rbm.py:347-356
-    const float t = fabsf(w) + 0.001f;
+    // (~1 ulp) instead of three IEEE divisions (they were 30 % of the fused kernel's instructions)      src/rbm.py:347-356
+    const float t = __fadd_rn(fabsf(w), 0.001f);
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + u.c1));
-    const float invD = t * r;
-    g *= invD;
-    mult *= invD;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(t, u.c1)));
+    const float invD = __fmul_rn(t, r);
+    g = __fmul_rn(g, invD);
+    mult = __fmul_rn(mult, invD);
   }
-  s_out = g + (s - g) * u.mom;
-  w_out = w * mult + s * u.lr;     // OLD speed: Theano updates are simultaneous (App. C-1)
+  s_out = __fmaf_rn(__fsub_rn(s, g), u.mom, g);
+  w_out = __fmaf_rn(w, mult, __fmul_rn(s, u.lr));     // OLD speed: Theano updates are simultaneous (App. C-1)
 }
 #endif
 

@@ -73,7 +73,18 @@ struct EpiParams {
   const float* uSnap;
   int uldw;
   UpdateScalars u;
+  // ... with one extra row (m == uV: the visible "unit" that is always 1 -> sum_b ph - nh, the hidden-bias gradient) and
+  // one extra column (n == uH: the hidden unit that is always 1 -> sum_b v0 - nv, the visible-bias gradient)
+  int uV, uH;
+  float *uhb, *uShb, *uvb, *uSvb;
+  float inv_rows;
 };
+// bias + speed from the raw gradient sum d (src/rbm.py:416-417, :361-364)
+__device__ __forceinline__ void update_bias_one(const EpiParams& ep, float* b, float* S, float d) {
+  const float g = d * ep.inv_rows, s = *S;
+  *S = g + (s - g) * ep.u.mom;
+  *b = *b + s * ep.u.lr;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // sigmoid on the MUFU pipe (ex2.approx + rcp.approx, a few ulp — far inside the 2e-3 bar of the TF32 path)
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
       if (EPI == EPI_UPDATE) {
         const int ncols = min(BN, ep.uldw - n0);
         if (ncols > 0) {
-          for (int r = lane; r < BM && m0 + r < M; r += 32) {
+          for (int r = lane; r < BM && m0 + r < ep.uV; r += 32) {
             const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
@@ -418,19 +429,19 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
         const int n = n0 + c * 16 + tcol;
         if (nkb <= 0) continue;
         if (EPI == EPI_UPDATE) {
-          // The loads of all row segments are issued before the first use (the tile comes from L2 at best, HBM at
-          // worst).  Padding columns n >= N of W (zeros) are left alone: with a 3-D operand box their statistics are
-          // not the TMA's out-of-bounds zeros.
-          if (n < N) {
-            const bool hs = ep.uSnap != nullptr, whole = n + 4 <= N;
+          // The tile is rows m <= V (m == V: the all-ones visible unit) x columns n <= H (n == H: the all-ones hidden
+          // unit).  W loads of all row segments are issued before the first use (the tile comes from L2 at best, HBM
+          // at worst); padding columns of W (zeros) are left alone.
+          if (n <= ep.uH) {
+            const bool hs = ep.uSnap != nullptr, whole = n + 4 <= ep.uH, wquad = n < ep.uldw;
             float4 w4[4], s4[4], n4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int m = m0 + quarter * 32 + 8 * i + trow;
-              const size_t o = (size_t)min(m, M - 1) * ep.uldw + n;
-              w4[i] = *reinterpret_cast<const float4*>(ep.uW + o);
-              s4[i] = *reinterpret_cast<const float4*>(ep.uS + o);
-              n4[i] = hs ? *reinterpret_cast<const float4*>(ep.uSnap + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const size_t o = (size_t)min(m, ep.uV - 1) * ep.uldw + n;
+              w4[i] = wquad ? *reinterpret_cast<const float4*>(ep.uW + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+              s4[i] = wquad ? *reinterpret_cast<const float4*>(ep.uS + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+              n4[i] = (hs && wquad) ? *reinterpret_cast<const float4*>(ep.uSnap + o) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -438,6 +449,13 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
               const int m = m0 + quarter * 32 + row;
               if (m >= M) continue;
               const float4 a4v = *reinterpret_cast<const float4*>(T + row * TLD + tcol);
+              const float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
+              if (m == ep.uV) {                                   // hidden-bias row
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt)
+                  if (n + tt < ep.uH) update_bias_one(ep, ep.uhb + n + tt, ep.uShb + n + tt, a4[tt]);
+                continue;
+              }
               float4 wo, so;
               update_one(ep.u, a4v.x, w4[i].x, s4[i].x, n4[i].x, hs, wo.x, so.x);
               update_one(ep.u, a4v.y, w4[i].y, s4[i].y, n4[i].y, hs, wo.y, so.y);
@@ -450,8 +468,10 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
               } else {
                 const float wf[4] = {wo.x, wo.y, wo.z, wo.w}, sf[4] = {so.x, so.y, so.z, so.w};
 #pragma unroll
-                for (int tt = 0; tt < 4; ++tt)
-                  if (n + tt < N) { ep.uW[o + tt] = wf[tt]; ep.uS[o + tt] = sf[tt]; }
+                for (int tt = 0; tt < 4; ++tt) {
+                  if (n + tt < ep.uH) { ep.uW[o + tt] = wf[tt]; ep.uS[o + tt] = sf[tt]; }
+                  else if (n + tt == ep.uH) update_bias_one(ep, ep.uvb + m, ep.uSvb + m, a4[tt]);      // visible-bias column
+                }
               }
             }
           }
@@ -672,11 +692,24 @@ static int n_slices(int K, int splits) {
 // ---- small ld-aware helpers of the tensor path ----------------------------------
 // rows b >= B of the batch tile (the statistics GEMM negates the nv/nh half per 32-row K block, so a minibatch that is
 // not a multiple of 32 is padded with zero rows) are written as zeros
+// The gather also plants the all-ones units of the statistics GEMM: column V of both halves of XV and column H of both
+// halves of YH are 1 in the rows of the minibatch (0 in the padding rows), so that row V / column H of
+// [v0;nv]^T (+/-) [ph;nh] are the bias gradients sum_b (ph - nh) and sum_b (v0 - nv).
+__device__ __forceinline__ void plant_ones(int b, int B, int Bp, float* XV, long long ldx, int V, float* YH, long long ldy,
+                                           int H) {
+  const float one = b < B ? 1.f : 0.f;
+  XV[(size_t)b * ldx + V] = one;
+  XV[(size_t)(Bp + b) * ldx + V] = one;
+  YH[(size_t)b * ldy + H] = one;
+  YH[(size_t)(Bp + b) * ldy + H] = one;
+}
 __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
-                                      int V, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
+                                      int Bp, int V, float* __restrict__ out, long long ldo, float* __restrict__ xi,
+                                      float* __restrict__ YH, long long ldy, int H) {
   const int b = blockIdx.y;      // rows b >= B are the zero padding
   const bool real = b < B;
   const float* src = data + (real ? (idx ? idx[b] : b) : 0) * ld;
+  if (blockIdx.x == 0 && threadIdx.x == 0) plant_ones(b, B, Bp, out, ldo, V, YH, ldy, H);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
     const float x = real ? __ldg(src + i) : 0.f;
     out[(size_t)b * ldo + i] = x;
@@ -685,13 +718,15 @@ __global__ void gather_rows_ld_kernel(const float* __restrict__ data, long long 
 }
 // the same, four columns per thread (V, strides and pointers multiples of 4 / 16 bytes): one row per blockIdx.y
 __global__ void gather_rows_ld4_kernel(const float* __restrict__ data, long long ld, const int* __restrict__ idx, int B,
-                                       int V4, float* __restrict__ out, long long ldo, float* __restrict__ xi) {
+                                       int Bp, int V4, float* __restrict__ out, long long ldo, float* __restrict__ xi,
+                                       float* __restrict__ YH, long long ldy, int H) {
   const int b = blockIdx.y;
   const bool real = b < B;
   const long long r = real ? (idx ? idx[b] : b) : 0;
   const float4* src = reinterpret_cast<const float4*>(data + r * ld);
   float4* dst = reinterpret_cast<float4*>(out + (size_t)b * ldo);
   float4* dx = xi ? reinterpret_cast<float4*>(xi + (size_t)b * ldo) : nullptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) plant_ones(b, B, Bp, out, ldo, 4 * V4, YH, ldy, H);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V4; i += gridDim.x * blockDim.x) {
     const float4 x = real ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     dst[i] = x;
@@ -738,6 +773,7 @@ static int col_diff_sum(mdbn_ctx* c, const float* X, long long ld, int B, int Bp
   c->launches += 2;
   return 0;
 }
+// (plain TF32 mode only: the split mode gets the bias gradients from the statistics GEMM)
 // Both bias gradients of a step with a moderate batch in ONE launch: column n < H is a hidden unit (rows of YH), the
 // rest are visible units (rows of XV); sum over the rows of (positive - negative), then either the raw sum goes to the
 // packed statistics (gsum != NULL) or the bias and its speed are updated in place (src/rbm.py:416-417, :361-364).
@@ -831,26 +867,39 @@ __global__ void sum_tree_kernel(const float* __restrict__ partial, int n, float*
     if (bit_idx) *bit_idx = (*bit_idx + 1) % V;
   }
 }
-__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
+// Split-K statistics [splits][V+1][H+1] (row V / column H: the bias gradients) summed in fixed order.
+// STATS (data-parallel shard): scattered into the packed buffer [V*H | H | V].
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int V, int H, int ones, float* __restrict__ G) {
+  const int H1 = H + ones;
+  const long long n = (long long)(V + ones) * H1;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + e];
-    out[e] = s;
+    const int i = (int)(e / H1), j = (int)(e - (long long)i * H1);
+    float g = 0.f;
+    for (int z = 0; z < splits; ++z) g += part[(size_t)z * n + e];
+    if (i < V && j < H) G[(size_t)i * H + j] = g;
+    else if (i == V && j < H) G[(size_t)V * H + j] = g;
+    else if (j == H && i < V) G[(size_t)V * H + H + i] = g;
   }
 }
-// split-K statistics of a full step: partials summed in fixed order and the update applied in the same pass
-__global__ void reduce_update_kernel(const float* __restrict__ part, int splits, int V, int H, float* __restrict__ W,
-                                     float* __restrict__ S, const float* __restrict__ Wsnap, int ldw, UpdateScalars u) {
-  const long long total = (long long)V * H;
+// Full step: the update of W / W_speed and of both biases rides on the reduction of the partials.
+__global__ void reduce_update_kernel(const float* __restrict__ part, int splits, int V, int H, int ones, EpiParams ep) {
+  const int H1 = H + ones;
+  const long long total = (long long)(V + ones) * H1;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e / H), j = (int)(e - (long long)i * H);
+    const int i = (int)(e / H1), j = (int)(e - (long long)i * H1);
     float g = 0.f;
     for (int z = 0; z < splits; ++z) g += part[(size_t)z * total + e];
-    const size_t o = (size_t)i * ldw + j;
-    float wo, so;
-    update_one(u, g, W[o], S[o], Wsnap ? Wsnap[o] : 0.f, Wsnap != nullptr, wo, so);
-    W[o] = wo;
-    S[o] = so;
+    if (i < V && j < H) {
+      const size_t o = (size_t)i * ep.uldw + j;
+      float wo, so;
+      update_one(ep.u, g, ep.uW[o], ep.uS[o], ep.uSnap ? ep.uSnap[o] : 0.f, ep.uSnap != nullptr, wo, so);
+      ep.uW[o] = wo;
+      ep.uS[o] = so;
+    } else if (i == V && j < H) {
+      update_bias_one(ep, ep.uhb + j, ep.uShb + j, g);
+    } else if (j == H && i < V) {
+      update_bias_one(ep, ep.uvb + i, ep.uSvb + i, g);
+    }
   }
 }
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
@@ -866,7 +915,7 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, f
 static int vec_ok(const EpiParams& ep, int N) {
   uintptr_t a = (uintptr_t)ep.bias | (uintptr_t)ep.pre | (uintptr_t)ep.mean | (uintptr_t)ep.sample |
                 (ep.rs.mode == MDBN_RNG_BUFFER ? (uintptr_t)ep.rs.seg : 0);
-  return N % 4 == 0 && ep.ld_pre % 4 == 0 && (a & 15) == 0;
+  return N % 4 == 0 && ep.ld_pre % 4 == 0 && ep.ld_mean % 4 == 0 && ep.ld_sample % 4 == 0 && (a & 15) == 0;
 }
 // one propagation: the GEMM with the fused epilogue, or — skinny shapes — split-K partials + the reduction kernel
 // that applies the same epilogue
@@ -892,11 +941,11 @@ static int propagate(mdbn_ctx* c, bool split3, const Operand& A, const Operand& 
   return 0;
 }
 static int up(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* hb, int B, int V, int H, const float* x,
-              long long ldx, bool x_exact, float* pre, float* mean, float* sample, long long ldo, const RngSeg& rs,
-              cudaStream_t st) {
+              long long ldx, bool x_exact, float* pre, float* mean, float* sample, long long ldo, long long ld_s,
+              const RngSeg& rs, cudaStream_t st) {
   EpiParams ep{};
   ep.bias = hb; ep.act = ACT_SIGMOID; ep.smp = sample ? SMP_BERNOULLI : SMP_NONE; ep.rs = rs;
-  ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ep.ld_sample = ldo;
+  ep.pre = pre; ep.mean = mean; ep.sample = sample; ep.ld_pre = ep.ld_mean = ldo; ep.ld_sample = ld_s;
   return propagate<true>(c, split3, Operand{x, ldx, false, x_exact, false}, Operand{W, ldw, true, false, false}, B, H, V, ep, st);
 }
 static int down(mdbn_ctx* c, bool split3, const float* W, int ldw, const float* vb, int B, int V, int H, int kind, int noisy,
@@ -918,7 +967,7 @@ bool tensor_phase_supported(const void* W, int ldw, const void* x, long long ldx
 // single-phase calls: fp32-exact (SPLIT) unless the context allows plain TF32 (mdbn_set_tf32_phases)
 int tensor_propup(mdbn_ctx* c, const float* W, int ldw, const float* hb, const float* v, int ldv, int B, int V, int H,
                   float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st) {
-  return tc::up(c, !c->tf32_phases, W, ldw, hb, B, V, H, v, ldv, false, pre, mean, sample, H, rs, st);
+  return tc::up(c, !c->tf32_phases, W, ldw, hb, B, V, H, v, ldv, false, pre, mean, sample, H, H, rs, st);
 }
 int tensor_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vb, const float* h, int ldh, int B, int V, int H,
                     int kind, int noisy, float* pre, float* mean, float* sample, const RngSeg& rs, cudaStream_t st) {
@@ -953,15 +1002,16 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   const bool split3 = !a.tf32;                 // fp32-exact unless the caller allows plain TF32
   const bool full = a.phase == MDBN_PHASE_FULL;
   const long long VH = (long long)V * H;
-  const long long ldx = (V + 3) & ~3, ldy = (H + 3) & ~3;
+  // activation scratch: one spare column behind the V visible / H hidden units for the all-ones unit (plant_ones)
+  const long long ldx = (V + 1 + 3) & ~3, ldy = (H + 1 + 3) & ~3, ldhs = (H + 3) & ~3;
   float* G = full ? nullptr : a.stats_buf;
   MDBN_CHECK(full || G != nullptr, "cd_step: stats buffer missing");
   float* XV = (float*)ws_get(c, WS_XV, (size_t)2 * Bp * ldx * sizeof(float));
   float* YH = (float*)ws_get(c, WS_YH, (size_t)2 * Bp * ldy * sizeof(float));
   // PCD chain state: the caller's [B, H] array IS the chain buffer when its row stride suits TMA (H % 4 == 0, 16-byte
   // aligned): the Gibbs steps read and overwrite it in place, no copy in, no copy out (src/rbm.py:308-311, :369)
-  const bool chain_in_place = a.persistent != nullptr && ldy == H && (((uintptr_t)a.persistent) & 15) == 0;
-  float* HS = chain_in_place ? a.persistent : (float*)ws_get(c, WS_HS, (size_t)B * ldy * sizeof(float));
+  const bool chain_in_place = a.persistent != nullptr && ldhs == H && (((uintptr_t)a.persistent) & 15) == 0;
+  float* HS = chain_in_place ? a.persistent : (float*)ws_get(c, WS_HS, (size_t)B * ldhs * sizeof(float));
   float* VS = (float*)ws_get(c, WS_VS, (size_t)B * ldx * sizeof(float));
   float* PREV = (float*)ws_get(c, WS_PREV, (size_t)B * ldx * sizeof(float));
   float* RED = (float*)ws_get(c, WS_RED, (size_t)(B > 4096 ? B : 4096) * sizeof(float));
@@ -977,12 +1027,13 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
   const int eb = 4 * c->num_sms;
   float* nv_mean = XV + (size_t)Bp * ldx;
   float* nh_mean = YH + (size_t)Bp * ldy;
-  // v0 = data[indices] (+ round(v0) for the pseudo-likelihood); the padding rows of v0 are written as zeros
+  // v0 = data[indices] (+ round(v0) for the pseudo-likelihood) and the all-ones units; padding rows are written as zeros
   if (V % 4 == 0 && a.ld_data % 4 == 0 && (((uintptr_t)a.data) & 15) == 0)
-    gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V / 4, XV,
-                                                                                    ldx, XI);
+    gather_rows_ld4_kernel<<<dim3((V / 4 + 255) / 256, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, Bp, V / 4,
+                                                                                    XV, ldx, XI, YH, ldy, H);
   else
-    gather_rows_ld_kernel<<<dim3((V + 1023) / 1024, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, V, XV, ldx, XI);
+    gather_rows_ld_kernel<<<dim3((V + 1023) / 1024, pcd ? B : Bp), 256, 0, st>>>(a.data, a.ld_data, a.indices, B, Bp, V, XV, ldx,
+                                                                                 XI, YH, ldy, H);
   c->launches++;
   if (Bp != B) {
     if (pcd) MDBN_CUDA(cudaMemsetAsync(XV + (size_t)B * ldx, 0, (size_t)(Bp - B) * ldx * sizeof(float), st));   // (XI has B rows)
@@ -991,24 +1042,24 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     c->launches++;
   }
   // positive phase
-  MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XV, ldx, false, nullptr, YH, pcd ? nullptr : HS, ldy,
+  MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XV, ldx, false, nullptr, YH, pcd ? nullptr : HS, ldy, ldhs,
               make_seg(a.rng, ul.off_h0, 0), st));
   if (pcd) {
-    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XI, ldx, false, PREX, nullptr, nullptr, ldy, make_seg(a.rng, 0, 0),
-                st));
+    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, XI, ldx, false, PREX, nullptr, nullptr, ldy, ldhs,
+                make_seg(a.rng, 0, 0), st));
     if (!chain_in_place) {
-      copy_rows_kernel<<<eb, 256, 0, st>>>(a.persistent, H, HS, ldy, B, H);      // chain state, padded stride for TMA
+      copy_rows_kernel<<<eb, 256, 0, st>>>(a.persistent, H, HS, ldhs, B, H);      // chain state, padded stride for TMA
       c->launches++;
     }
   }
   for (int s = 0; s < k; ++s) {
     long long base = (long long)B * H + s * ul.step_stride;
     // (the chain state is {0,1} once this step has sampled it; a caller-provided persistent chain is not assumed to be)
-    MDBN_TRY(down(c, split3, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldy, !(pcd && s == 0),
+    MDBN_TRY(down(c, split3, a.W, a.ldw, a.vbias, B, V, H, a.kind, a.noisy, HS, ldhs, !(pcd && s == 0),
                   a.kind == MDBN_GRBM ? nullptr : PREV, nv_mean,
                   a.kind == MDBN_RBM ? VS : nullptr, ldx, make_seg(a.rng, base + ul.off_v, ord_v(s)), st));
     const float* v_in = a.kind == MDBN_GRBM ? nv_mean : VS;
-    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, v_in, ldx, a.kind == MDBN_RBM, nullptr, nh_mean, HS, ldy,
+    MDBN_TRY(up(c, split3, a.W, a.ldw, a.hbias, B, V, H, v_in, ldx, a.kind == MDBN_RBM, nullptr, nh_mean, HS, ldy, ldhs,
                 make_seg(a.rng, base + ul.off_h, ord_h(s)), st));
   }
   // monitoring cost on the OLD parameters (src/rbm.py:367-374), before anything is updated
@@ -1018,10 +1069,10 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
     float* cost = full ? a.cost_out : nullptr;
     if (pcd) {
       pl_row_ld_kernel<<<B, 128, 0, st>>>(PREX, ldy, H, XI, ldx, V, a.W, a.ldw, a.vbias, a.bit_i_idx, a.kind, RED);
-      sum_tree_kernel<<<1, 256, 0, st>>>(RED, B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, a.bit_i_idx, V);
+      sum_tree_kernel<<<1, 1024, 0, st>>>(RED, B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, a.bit_i_idx, V);
       c->launches += 2;
       if (!chain_in_place) {
-        copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldy, a.persistent, H, B, H);
+        copy_rows_kernel<<<eb, 256, 0, st>>>(HS, ldhs, a.persistent, H, B, H);
         c->launches++;
       }
     } else {
@@ -1029,59 +1080,69 @@ int tensor_cd_step(mdbn_ctx* c, const mdbn_cd_args& a, cudaStream_t st) {
       int nbx = (V + 1023) / 1024;
       while ((long long)nbx * B > 4096) nbx = (nbx + 1) / 2;
       recon_cost_ld_kernel<<<dim3(nbx, B), 256, 0, st>>>(a.kind == MDBN_GRBM ? nv_mean : PREV, XV, ldx, B, V, a.kind, RED);
-      sum_tree_kernel<<<1, 256, 0, st>>>(RED, nbx * B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, nullptr, V);
+      sum_tree_kernel<<<1, 1024, 0, st>>>(RED, nbx * B, num, (float)B, num ? num + 1 : nullptr, cost, 1.0f / den, nullptr, V);
       c->launches += 2;
     }
   }
-  // statistics: [v0;nv]^T (+/-) [ph;nh] over K = 2 Bp.  A full step with enough output tiles applies the update in the
-  // GEMM's epilogue; few tiles (small layers, large batch) split K across the SMs and the update rides on the reduction
-  // of the partials.  STATS (data-parallel shard): the packed buffer gets the raw sums.
+  // statistics: [v0;nv;1]^T (+/-) [ph;nh;1] over K = 2 Bp.  In the fp32-exact mode the extra row and column (the all-ones
+  // units) are the bias gradients; plain TF32 would truncate v0 / nv / ph / nh inside those sums — differences of nearly
+  // equal numbers — so that mode keeps its exact fp32 column sums (bias_tail_kernel / col_diff_sum).  A full step with
+  // enough output tiles applies the update of W, W_speed (and the biases) in the GEMM's epilogue; few tiles (small
+  // layers, large batch) split K across the SMs and the update rides on the reduction of the partials.  STATS
+  // (data-parallel shard): the packed buffer gets the raw sums.
   {
-    const int tiles = ((V + BM - 1) / BM) * ((H + BN - 1) / BN);
+    const int ones = split3 ? 1 : 0;
+    const int V1 = V + ones, H1 = H + ones;
+    const int tiles = ((V1 + BM - 1) / BM) * ((H1 + BN - 1) / BN);
     const int nkb = 2 * Bp / BK;
     const int slots = c->num_sms * (split3 ? 1 : 2);
     int splits = 1;
     if (2 * tiles <= slots) {
-      splits = (slots + tiles - 1) / tiles;
+      splits = slots / tiles;          // (floor: one round of resident CTAs, never a ragged second one)
       if (splits > nkb / 2) splits = nkb / 2 > 0 ? nkb / 2 : 1;
       if (splits > 32) splits = 32;
     }
     const Operand Ao{XV, ldx, true, false, true}, Bo{YH, ldy, true, false, true};
-    const UpdateScalars u = make_update_scalars(a);
-    const float* snap = a.weightcost != 0.f ? a.W_snap : nullptr;
+    EpiParams ep{};
+    ep.uW = a.W; ep.uS = a.W_speed; ep.uSnap = a.weightcost != 0.f ? a.W_snap : nullptr; ep.uldw = a.ldw;
+    ep.u = make_update_scalars(a);
+    ep.uV = V; ep.uH = ones ? H : H + (1 << 20);      // (no all-ones column: n == uH never happens)
+    ep.uhb = a.hbias; ep.uShb = a.hbias_speed; ep.uvb = a.vbias; ep.uSvb = a.vbias_speed;
+    ep.inv_rows = 1.0f / (float)B;
     if (full && splits == 1) {
-      EpiParams ep{};
-      ep.uW = a.W; ep.uS = a.W_speed; ep.uSnap = snap; ep.uldw = a.ldw; ep.u = u;
-      MDBN_TRY((launch_gemm<true, true, EPI_UPDATE>(c, split3, Ao, Bo, V, H, 2 * Bp, 1, Bp, ep, st)));
+      MDBN_TRY((launch_gemm<true, true, EPI_UPDATE>(c, split3, Ao, Bo, V1, H1, 2 * Bp, 1, Bp, ep, st)));
     } else {
       const int zs = n_slices(2 * Bp, splits);
-      float* part = (float*)ws_get(c, WS_PART, (size_t)zs * VH * sizeof(float));
+      float* part = (float*)ws_get(c, WS_PART, (size_t)zs * V1 * H1 * sizeof(float));
       if (!part) return 3;
-      EpiParams ep{};
-      ep.part = part;
-      ep.vec4 = H % 4 == 0;
-      MDBN_TRY((launch_gemm<true, true, EPI_PART>(c, split3, Ao, Bo, V, H, 2 * Bp, splits, Bp, ep, st)));
-      if (full) reduce_update_kernel<<<eb, 256, 0, st>>>(part, zs, V, H, a.W, a.W_speed, snap, a.ldw, u);
-      else reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, VH, G);
+      EpiParams pp{};
+      pp.part = part;
+      pp.vec4 = H1 % 4 == 0;
+      MDBN_TRY((launch_gemm<true, true, EPI_PART>(c, split3, Ao, Bo, V1, H1, 2 * Bp, splits, Bp, pp, st)));
+      if (full) reduce_update_kernel<<<eb, 256, 0, st>>>(part, zs, V, H, ones, ep);
+      else reduce_parts_kernel<<<eb, 256, 0, st>>>(part, zs, V, H, ones, G);
       c->launches++;
       if (!full && c->ev_stats_w) { MDBN_CUDA(cudaEventRecord(c->ev_stats_w, st)); c->ev_stats_w_done = true; }
     }
-  }
-  // bias gradients: raw sums into the packed buffer (STATS) or the in-place update (full step)
-  if (B <= 1024) {
-    bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, nullptr, full ? nullptr : G + VH, a.hbias,
-                                                          a.hbias_speed, a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum,
-                                                          a.lr);
-    c->launches++;
-  } else {
-    float* gs = full ? (float*)ws_get(c, WS_G, (size_t)(H + V) * sizeof(float)) : G + VH;
-    if (!gs) return 3;
-    MDBN_TRY(col_diff_sum(c, YH, ldy, B, Bp, H, gs, st));
-    MDBN_TRY(col_diff_sum(c, XV, ldx, B, Bp, V, gs + H, st));
-    if (full) {
-      bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, gs, nullptr, a.hbias, a.hbias_speed,
-                                                            a.vbias, a.vbias_speed, 1.0f / (float)B, a.momentum, a.lr);
-      c->launches++;
+    if (!ones) {
+      // plain TF32: exact fp32 bias gradients, raw sums into the packed buffer (STATS) or the in-place update (full step)
+      if (B <= 1024) {
+        bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, nullptr, full ? nullptr : G + VH,
+                                                            a.hbias, a.hbias_speed, a.vbias, a.vbias_speed, 1.0f / (float)B,
+                                                            a.momentum, a.lr);
+        c->launches++;
+      } else {
+        float* gs = full ? (float*)ws_get(c, WS_G, (size_t)(H + V) * sizeof(float)) : G + VH;
+        if (!gs) return 3;
+        MDBN_TRY(col_diff_sum(c, YH, ldy, B, Bp, H, gs, st));
+        MDBN_TRY(col_diff_sum(c, XV, ldx, B, Bp, V, gs + H, st));
+        if (full) {
+          bias_tail_kernel<<<(H + V + 31) / 32, 256, 0, st>>>(YH, ldy, H, XV, ldx, V, B, Bp, gs, nullptr, a.hbias,
+                                                              a.hbias_speed, a.vbias, a.vbias_speed, 1.0f / (float)B,
+                                                              a.momentum, a.lr);
+          c->launches++;
+        }
+      }
     }
   }
   MDBN_CUDA(cudaGetLastError());
