@@ -1,12 +1,12 @@
-# Multi-GPU lines of profiles/ (run under `gpurun --gpus 4`)
+# Multi-GPU lines of profiles/ (run under `gpurun --gpus N`, N = 2, 4 or 8): the driver-style bench line (weak scaling of the
+# default workload + mdbn_aml_wallclock_s + the data-parallel legs) and the config-5 sweep sharded over the N ranks.
 set -x
-mkdir -p gpurun_out/mg
+N=${1:-2}
+O=gpurun_out/mg
+mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-for n in 2 4; do
-  $TR --nproc-per-node $n --master-port $((29500+n)) bench.py --gpus $n --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/mg/bench_n$n.json
-  $TR --nproc-per-node $n --master-port $((29600+n)) bench.py --gpus $n --workload rbm_784x500_b8192_pcd1_tf32 --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/mg/dp_n$n.json
-done
-python bench.py --workload rbm_784x500_b8192_pcd1_tf32 --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/mg/dp_n1.json
-python scripts/mdbn_aml_wallclock.py 2>/dev/null | tail -1 > gpurun_out/mg/mdbn_n1.json
-$TR --nproc-per-node 3 --master-port 29710 scripts/mdbn_aml_wallclock.py 2>/dev/null | tail -1 > gpurun_out/mg/mdbn_n3.json
-head -c 300 gpurun_out/mg/*.json
+$TR --nproc-per-node $N --master-port $((29500+N)) bench.py --gpus $N --steps 204 --warmup 34 --no-cpu-baseline 2> $O/bench_n$N.err | tail -1 > $O/bench_n$N.json
+if [ "$2" = "sweep" ]; then
+  $TR --nproc-per-node $N --master-port $((29600+N)) scripts/config_sweeps.py 2> $O/sweep_n$N.err | tail -1 > $O/config_sweeps_n$N.json
+fi
+head -c 600 $O/bench_n$N.json

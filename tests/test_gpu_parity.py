@@ -176,6 +176,7 @@ CONFIG_SHAPES = [
     ("mid_dbn_b64_cd1", O.RBM, 1000, 1000, 64, 1, False, 0.01, 0.9, 0.0, 0.0, 0.0002),
     ("mid_odd_b37_pcd2", O.GRBM, 1203, 76, 37, 2, True, 0.005, 0.3, 0.02, 0.05, 0.001),
     ("mid_b21_cd1", O.RBM, 640, 128, 21, 1, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
+    ("big_mnist_b1024_pcd2", O.RBM, 784, 500, 1024, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
     ("odd_shapes", O.RBM, 77, 13, 7, 3, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
     ("odd_shapes_g", O.GRBM, 131, 30, 3, 2, True, 0.01, 0.3, 0.02, 0.05, 0.001),
 ]
@@ -505,8 +506,8 @@ def test_size_independent_properties_full_size():
 TF32_RTOL = 2e-3
 
 
-@pytest.mark.parametrize("shape", [(128, 784, 500), (64, 200, 72), (70, 132, 52), (256, 1000, 1000), (32, 100, 24)],
-                         ids=lambda s: "B%d_V%d_H%d" % s)
+@pytest.mark.parametrize("shape", [(128, 784, 500), (64, 200, 72), (70, 132, 52), (256, 1000, 1000), (32, 100, 24),
+                                   (1024, 784, 500), (8192, 784, 500)], ids=lambda s: "B%d_V%d_H%d" % s)
 @pytest.mark.parametrize("kind", [O.RBM, O.GRBM])
 def test_tensor_phases_vs_oracle(shape, kind):
     B, V, H = shape
@@ -601,6 +602,9 @@ TENSOR_STEPS = [
     ("rbm_784x500_b256_pcd2", O.RBM, 784, 500, 256, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
     ("grbm_1000x64_b64_cd1", O.GRBM, 1000, 64, 64, 1, False, 0.005, 0.0, 0.01, 0.1, 0.0),
     ("grbm_2000x400_b96_pcd1", O.GRBM, 2000, 400, 96, 1, True, 0.005, 0.0, 0.01, 0.1, 0.0),
+    # the benchmarked large-batch regime (BASELINE configs[4]): many chains, k = 10
+    ("rbm_784x500_b1024_pcd10", O.RBM, 784, 500, 1024, 10, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
+    ("rbm_784x500_b8192_pcd2", O.RBM, 784, 500, 8192, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
 ]
 
 
@@ -631,10 +635,11 @@ def test_tensor_cd_step_tracks_oracle(cfg):
                      (r.vbias_speed.get_value(), L.vbias_speed, "vb_speed")):
         # floor: z-scored minibatches have exactly-zero column means, so a speed can be pure round-off
         rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-3 * np.sqrt(b.size))
-        assert rel < 1e-2, "%s relative error %.3e" % (nm, rel)
+        # (a long chain compounds the flipped draws: every flipped hidden bit shifts the next visible probabilities)
+        assert rel < (1e-2 if k <= 2 else 3e-2), "%s relative error %.3e" % (nm, rel)
     close(r.W.get_value(), L.W, rtol=1e-5, scale=np.abs(L.W).max(), what="W (first step moves W by mult only)")
     if Po is not None:
-        assert (P.get_value() != Po).mean() < 0.02
+        assert (P.get_value() != Po).mean() < (0.02 if k <= 2 else 0.1)
 
 
 # ---------------------------------------------------------------------------
