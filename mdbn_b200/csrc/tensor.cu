@@ -252,6 +252,20 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
     nkb = min(nkb_total, kb_begin + kb_per_split) - kb_begin;
   };
 
+  // The W / W_speed (/ W_snap) tile an update item will read-modify-write: pulled into L2 while its mainloop runs, one row
+  // per thread of a group of `nthr` otherwise idle threads (NOT the producer warp: the bulk-prefetch instruction runs on
+  // the uniform datapath, lane after lane, and 256 of them in front of an item's TMA loads cost it 6-9 us)
+  auto prefetch_tile = [&](int m0, int n0, int t0, int nthr) {
+    const int ncols = min(BN, ep.uldw - n0);
+    if (ncols <= 0) return;
+    for (int r = t0; r < BM && m0 + r < ep.uV; r += nthr) {
+      const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
+      if (ep.uSnap) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uSnap + o), "r"(ncols * 4) : "memory");
+    }
+  };
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -276,22 +290,11 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (lane 0); the whole warp first asks L2 for the W / W_speed tile of an update item =====
+    // ===== TMA producer (lane 0) =====
     int g = 0;      // k-blocks issued so far: ring position and phase
     for (int item = item0; item < n_items; item += item_step) {
       int m0, n0, bz, kb_begin, nkb;
       decode(item, m0, n0, bz, kb_begin, nkb);
-      if (EPI == EPI_UPDATE) {
-        const int ncols = min(BN, ep.uldw - n0);
-        if (ncols > 0) {
-          for (int r = lane; r < BM && m0 + r < ep.uV; r += 32) {
-            const size_t o = (size_t)(m0 + r) * ep.uldw + n0;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uW + o), "r"(ncols * 4) : "memory");
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uS + o), "r"(ncols * 4) : "memory");
-            if (ep.uSnap) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.uSnap + o), "r"(ncols * 4) : "memory");
-          }
-        }
-      }
       if (lane == 0) {
         for (int i = 0; i < nkb; ++i, ++g) {
           const int s = g % STAGES, it = g / STAGES;
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
       for (int item = item0; item < n_items; item += item_step) {
         int m0, n0, bz, kb_begin, nkb;
         decode(item, m0, n0, bz, kb_begin, nkb);
+        if (EPI == EPI_UPDATE) prefetch_tile(m0, n0, te, N_XFORM);
         for (int i = 0; i < nkb; ++i, ++g) {
           const int s = g % STAGES, it = g / STAGES;
           mbar_wait(full0 + 8 * s, it & 1);
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(n_threads(SPLIT), SPLIT ? 1 : 2)
       int m0, n0, bz, kb_begin, nkb;
       decode(item, m0, n0, bz, kb_begin, nkb);
       const int ab = SPLIT ? (t & 1) : 0;
+      if (EPI == EPI_UPDATE && !SPLIT) prefetch_tile(m0, n0, (int)threadIdx.x - 32 * EW0, 256);
       mbar_wait(tfull0 + 8 * ab, SPLIT ? ((t >> 1) & 1) : 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1

@@ -176,7 +176,6 @@ CONFIG_SHAPES = [
     ("mid_dbn_b64_cd1", O.RBM, 1000, 1000, 64, 1, False, 0.01, 0.9, 0.0, 0.0, 0.0002),
     ("mid_odd_b37_pcd2", O.GRBM, 1203, 76, 37, 2, True, 0.005, 0.3, 0.02, 0.05, 0.001),
     ("mid_b21_cd1", O.RBM, 640, 128, 21, 1, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
-    ("big_mnist_b1024_pcd2", O.RBM, 784, 500, 1024, 2, True, 0.1, 0.9, 0.0, 0.0, 0.0002),
     ("odd_shapes", O.RBM, 77, 13, 7, 3, False, 0.1, 0.5, 0.0, 0.0, 0.0002),
     ("odd_shapes_g", O.GRBM, 131, 30, 3, 2, True, 0.01, 0.3, 0.02, 0.05, 0.001),
 ]
@@ -553,7 +552,7 @@ def test_tensor_phases_vs_oracle(shape, kind):
 
 
 @pytest.mark.parametrize("shape", [(128, 784, 500), (10, 19937, 400), (100, 19937, 400), (70, 132, 52), (256, 1000, 1000),
-                                   (37, 1204, 76)], ids=lambda s: "B%d_V%d_H%d" % s)
+                                   (37, 1204, 76), (1024, 784, 500)], ids=lambda s: "B%d_V%d_H%d" % s)
 @pytest.mark.parametrize("kind", [O.RBM, O.GRBM])
 def test_split_tf32_phases_vs_oracle(shape, kind):
     """The single-phase calls (propup / propdown / free_energy, src/rbm.py:166-240, :647-688) run on the tcgen05 path in
