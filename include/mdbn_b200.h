@@ -27,10 +27,11 @@ typedef struct mdbn_comm mdbn_comm;   /* NCCL communicator of the data-parallel 
 
 enum { MDBN_RBM = 0, MDBN_GRBM = 1 };                       /* src/rbm.py:46 / :631 */
 enum { MDBN_RNG_NONE = 0, MDBN_RNG_BUFFER = 1, MDBN_RNG_PHILOX = 2 };
-/* AUTO picks by shape (full steps): TINY (one cluster, weights in shared memory: small layers), SKINNY (persistent
- * grid kernel, B <= 20), TENSOR (tcgen05 GEMMs with fused epilogues, any B > 20: fp32-exact split-TF32 arithmetic, or
+/* AUTO picks by shape (full steps): TINY (one cluster, weights in shared memory: small layers), MID (medium layers,
+ * B <= 20: column / row sliced propagations around broadcasts, W in L2), SKINNY (persistent row-slab grid kernel,
+ * B <= 20, wide layers), TENSOR (tcgen05 GEMMs with fused epilogues, any B > 20: fp32-exact split-TF32 arithmetic, or
  * plain TF32 with tf32 = 1), else GENERIC (fp32 SIMT: operands that do not suit TMA). */
-enum { MDBN_PATH_AUTO = 0, MDBN_PATH_GENERIC = 1, MDBN_PATH_SKINNY = 2, MDBN_PATH_TENSOR = 3, MDBN_PATH_TINY = 4 };
+enum { MDBN_PATH_AUTO = 0, MDBN_PATH_GENERIC = 1, MDBN_PATH_SKINNY = 2, MDBN_PATH_TENSOR = 3, MDBN_PATH_TINY = 4, MDBN_PATH_MID = 5 };
 enum { MDBN_PHASE_FULL = 0, MDBN_PHASE_STATS = 1, MDBN_PHASE_APPLY = 2 };
 
 /* Source of randomness for one call.

@@ -12,9 +12,9 @@ LIB_PATH = os.environ.get("MDBN_B200_LIB") or os.path.join(_HERE, "csrc", "libmd
 
 RBM, GRBM = 0, 1
 RNG_NONE, RNG_BUFFER, RNG_PHILOX = 0, 1, 2
-PATH_AUTO, PATH_GENERIC, PATH_SKINNY, PATH_TENSOR, PATH_TINY = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_GENERIC, PATH_SKINNY, PATH_TENSOR, PATH_TINY, PATH_MID = 0, 1, 2, 3, 4, 5
 PHASE_FULL, PHASE_STATS, PHASE_APPLY = 0, 1, 2
-PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "skinny": PATH_SKINNY, "tensor": PATH_TENSOR, "tiny": PATH_TINY}
+PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "skinny": PATH_SKINNY, "tensor": PATH_TENSOR, "tiny": PATH_TINY, "mid": PATH_MID}
 
 
 class MdbnError(RuntimeError):

@@ -1,4 +1,5 @@
 // C ABI (include/mdbn_b200.h): context management, argument validation, path dispatch.
+#include <stdlib.h>
 #include <string.h>
 #include "ctx.h"
 
@@ -95,6 +96,13 @@ long long mdbn_stats_size(int V, int H) { return (long long)V * H + H + V + 2; }
 // (one small launch either way).
 static bool tensor_phase_wanted(int V, int H) { return (long long)V * H >= 4096; }
 
+// AUTO takes the broadcast kernel (mid.cu) where the whole visible state of a minibatch fits in shared memory and the
+// layer is small enough for its column-sliced reads of W to stay in L2; wider layers stream row slabs (skinny.cu)
+static bool mid_wanted(const mdbn_ctx* c, const mdbn_cd_args& a) {
+  static const bool off = getenv("MDBN_NO_MID") != nullptr;
+  return !off && (long long)a.V * a.ldw <= (4LL << 20) && mid_supported(c, a);
+}
+
 static int check_common(const mdbn_ctx* c, const void* W, int ldw, int B, int V, int H) {
   MDBN_CHECK(c != nullptr, "ctx is NULL");
   MDBN_CHECK(W != nullptr, "W is NULL");
@@ -178,6 +186,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   int path = a->path;
   if (path == MDBN_PATH_AUTO) {
     if (a->phase == MDBN_PHASE_FULL && tiny_supported(c, *a)) path = MDBN_PATH_TINY;
+    else if (a->phase == MDBN_PHASE_FULL && mid_wanted(c, *a)) path = MDBN_PATH_MID;
     else if (a->phase == MDBN_PHASE_FULL && skinny_supported(c, *a)) path = MDBN_PATH_SKINNY;
     else if ((a->B > 20 || a->tf32) && tensor_supported(c, *a)) path = MDBN_PATH_TENSOR;   // fp32-exact unless tf32
     else path = MDBN_PATH_GENERIC;
@@ -193,6 +202,10 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
       MDBN_CHECK(tiny_supported(c, *a), "cd_step: tiny path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B, a->V, a->H,
                  a->ldw, a->phase);
       return tiny_cd_steps(c, *a, 1, st);
+    case MDBN_PATH_MID:
+      MDBN_CHECK(mid_supported(c, *a), "cd_step: mid path does not take B=%d V=%d H=%d ldw=%d phase=%d", a->B, a->V, a->H,
+                 a->ldw, a->phase);
+      return mid_cd_steps(c, *a, 1, st);
     case MDBN_PATH_TENSOR:
       MDBN_CHECK(tensor_supported(c, *a), "cd_step: tensor path does not take B=%d V=%d H=%d ldw=%d", a->B, a->V, a->H,
                  a->ldw);
@@ -214,7 +227,9 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
   const bool want_tiny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_TINY;
   const bool want_skinny = a->path == MDBN_PATH_AUTO || a->path == MDBN_PATH_SKINNY;
   const bool use_tiny = want_tiny && c && a->W && tiny_supported(c, *a);
-  if (use_tiny || (want_skinny && c && a->W && skinny_supported(c, *a))) {
+  const bool use_mid = !use_tiny && c && a->W && ((a->path == MDBN_PATH_AUTO && mid_wanted(c, *a)) ||
+                                                  (a->path == MDBN_PATH_MID && mid_supported(c, *a)));
+  if (use_tiny || use_mid || (want_skinny && c && a->W && skinny_supported(c, *a))) {
     MDBN_TRY(check_common(c, a->W, a->ldw, a->B, a->V, a->H));
     MDBN_CHECK(a->kind == MDBN_RBM || a->kind == MDBN_GRBM, "cd_steps: bad kind %d", a->kind);
     MDBN_CHECK(a->hbias && a->vbias && a->W_speed && a->hbias_speed && a->vbias_speed, "cd_steps: NULL parameter/state");
@@ -225,6 +240,7 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
     MDBN_CHECK(!a->persistent || a->bit_i_idx, "cd_steps: PCD needs bit_i_idx");
     MDBN_CUDA(cudaSetDevice(c->device));
     if (use_tiny) return tiny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
+    if (use_mid) return mid_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
     return skinny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
   }
   for (int s = 0; s < n_steps; ++s) {

@@ -87,6 +87,10 @@ int skinny_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t 
 bool tiny_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int tiny_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t st);
 
+// ---- medium layers at skinny batch: column / row sliced propagations around broadcasts, W in L2: mid.cu ----
+bool mid_supported(const mdbn_ctx*, const mdbn_cd_args& a);
+int mid_cd_steps(mdbn_ctx*, const mdbn_cd_args& a, int n_steps, cudaStream_t st);
+
 // ---- tcgen05 / TMA path (large batch, TF32): tensor.cu ----------------------
 bool tensor_supported(const mdbn_ctx*, const mdbn_cd_args& a);
 int tensor_cd_step(mdbn_ctx*, const mdbn_cd_args& a, cudaStream_t st);

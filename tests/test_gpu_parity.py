@@ -119,7 +119,7 @@ def run_cd_golden(g, path):
     return r, P, np.array(costs)
 
 
-@pytest.mark.parametrize("path", ["generic", "skinny", "tiny", "auto"])
+@pytest.mark.parametrize("path", ["generic", "skinny", "tiny", "mid", "auto"])
 @pytest.mark.parametrize("name", CD_CASES)
 def test_cd_sequences_vs_golden(name, path):
     g = load(name)
@@ -848,7 +848,7 @@ SMALL_CFGS = [c for c in CONFIG_SHAPES if c[0] in ("cfg4_me_cd10", "cfg4_top_cd1
     ("rbm_400x40_cd5", O.RBM, 400, 40, 20, 5, False, 0.1, 0.6, 0.0, 0.0, 0.0002)]
 
 
-@pytest.mark.parametrize("path", ["skinny", "tiny"])
+@pytest.mark.parametrize("path", ["skinny", "tiny", "mid"])
 @pytest.mark.parametrize("cfg", SMALL_CFGS, ids=[c[0] for c in SMALL_CFGS])
 def test_small_layers_both_kernels(cfg, path):
     test_config_shapes_vs_oracle(cfg, path)
@@ -857,7 +857,8 @@ def test_small_layers_both_kernels(cfg, path):
 @pytest.mark.parametrize("path,kind,pcd,k,B", [("skinny", O.GRBM, True, 4, 10), ("skinny", O.RBM, False, 5, 10),
                                                ("tiny", O.GRBM, False, 4, 10), ("tiny", O.RBM, True, 2, 10),
                                                ("skinny", O.RBM, True, 2, 20), ("skinny", O.GRBM, False, 1, 17),
-                                               ("tiny", O.GRBM, True, 3, 20)])
+                                               ("tiny", O.GRBM, True, 3, 20), ("mid", O.GRBM, True, 3, 20),
+                                               ("mid", O.RBM, False, 2, 13), ("mid", O.RBM, True, 1, 10)])
 def test_run_steps_deep_chains_both_kernels(path, kind, pcd, k, B):
     """Chained launches with k > 3 (the grid kernel re-zeroes and rotates its Gibbs accumulators inside a step and
     alternates the accumulator sets between the steps of one launch) == single-step launches, bitwise."""
