@@ -25,6 +25,7 @@ namespace md {
 
 constexpr int NT = 256, NWARP = NT / 32;
 constexpr int MAXB = 20;
+constexpr size_t MAX_SMEM = 227 * 1024;
 
 struct Params {
   float *W, *S;
@@ -44,6 +45,7 @@ struct Params {
   const float* ubuf;
   uint32_t k0, k1, c2, c3;
   long long u_step_stride, u_off_v, u_off_h;
+  int wcol_cached;                  // the own column quads of W stay in shared memory for a whole step
   int BTS, CQ, ldh, NQ, NR, HC;     // batch tile, column quads, padded H, own quads / rows per CTA, statistics column chunk
   float *Hg, *PHg, *NHg;            // [BTS][ldh] published hidden sample / positive means / negative means
   float* Vg;                        // [V][BTS]  published visible state (transposed)
@@ -61,14 +63,40 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast_(float x) { return rcp_approx(1.0f + __expf(-x)); }
 
+// Asynchronous global -> shared copies (LDGSTS): every request of a panel is in flight at once, no register staging.
+// .cg reads through L2 (panels and weights other CTAs have just written), .ca may keep the read-only dataset in L1.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Sum over the 32 lanes of v[0..MAXB) at once: lane L returns the warp total of v[L] (0 for L >= MAXB).  31 shuffles in
+// five levels instead of 5 per value; fixed order.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int s = 0; s < w; ++s) {
+      const float send = up ? v[s] : v[s + w], keep = up ? v[s + w] : v[s];
+      v[s] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
 // Device-wide barrier (all CTAs co-resident: cooperative launch); the counter is monotonic within a launch and reset by
 // the last CTA to leave the kernel.
 __device__ __forceinline__ void grid_sync(unsigned long long* bar, unsigned long long& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1ULL);
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");      // no round trip before the spin
     unsigned long long v;
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
@@ -91,13 +119,13 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);   // [64] block_sum scratch; [32..] minibatch row numbers
   float4* wcol = reinterpret_cast<float4*>(smem + p.off_wcol); // [V] one column quad of W, staged for a propup
 
+  float* hbo = misc + 32;                                      // [NQ][4] hidden biases of the own columns (this step's)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, G = gridDim.x;
   const int B = p.B, V = p.V, H = p.H, BTS = p.BTS, ldh = p.ldh, ldw = p.ldw;
   const int q0 = cta * p.NQ, nq = max(0, min(p.NQ, p.CQ - q0));      // own column quads
   const int i0 = cta * p.NR, nr = max(0, min(p.NR, V - i0));         // own visible rows
   unsigned long long bar_target = 0;
-  int* sidx = reinterpret_cast<int*>(misc) + 32;
   const int bit0 = p.pcd ? *p.bit_idx : 0;
   int dbg_i = 0;
   auto mark = [&]() {
@@ -107,24 +135,30 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       p.dbg[dbg_i++] = t;
     }
   };
+  if (p.dbg && cta == 0 && tid < 24) p.dbg[tid] = 0ULL;
   mark();
-  // global -> shared copy of n4 float4, eight L2 loads in flight per thread
+  // global -> shared copy of n4 float4 (both 16-byte aligned), all requests in flight at once; cp_async_wait() completes it
   auto copy_f4 = [&](float* dst, const float* src, int n4) {
-    constexpr int U = 8;
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int e0 = tid; e0 < n4; e0 += U * NT) {
-      float4 t[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int e = e0 + u * NT;
-        t[u] = e < n4 ? __ldcg(s4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int e = tid; e < n4; e += NT) cp_async16(d4 + e, s4 + e);
+  };
+
+  // The own rows of minibatch `step` (v0o, and published as rows of the [V][BTS] visible panel).  Every CTA reading the
+  // whole minibatch out of the dataset measured ~5 us whatever the access width; the panel copy after a barrier is 0.6 us,
+  // and in a chained launch the barrier is the one that ends the previous step anyway.
+  auto gather_slice = [&](int step) {
+    const int* idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
+    for (int e = tid; e < nr * BTS; e += NT) {
+      const int r = e / BTS, b = e - r * BTS;
+      float x = 0.f;
+      if (b < B) {
+        const long long row = idxp ? __ldg(idxp + b) : b;
+        x = __ldg(p.data + row * p.ld_data + i0 + r);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int e = e0 + u * NT;
-        if (e < n4) d4[e] = t[u];
-      }
+      v0o[e] = x;
+      __stcg(&p.Vg[(size_t)i0 * BTS + e], x);
     }
   };
 
@@ -148,17 +182,18 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-      // the column quad of all V rows: every thread fetches its share at once (one L2 round trip), then the sums run
-      // out of shared memory
-      {
+      // the column quad of all V rows out of shared memory: staged once per step (stage_columns) where the own quads fit,
+      // else fetched here, every thread its share at once (one L2 round trip)
+      const float4* wq = wcol + (p.wcol_cached ? (size_t)qq * V : 0);
+      if (!p.wcol_cached) {
         const float* wp = p.W + 4 * (q0 + qq);
         for (int i = tid; i < V; i += NT) wcol[i] = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)i * ldw));
+        __syncthreads();
       }
-      __syncthreads();
       if (ch < NCH) {
 #pragma unroll 4
         for (int i = ch; i < V; i += NCH) {
-          const float4 w = wcol[i];
+          const float4 w = wq[i];
           float4 v = *reinterpret_cast<const float4*>(vbuf + i * BTS + 4 * bg);
           if (rounded) v = make_float4(roundf(v.x), roundf(v.y), roundf(v.z), roundf(v.w));      // src/rbm.py:428
           const float vv[4] = {v.x, v.y, v.z, v.w}, ww[4] = {w.x, w.y, w.z, w.w};
@@ -190,6 +225,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
   auto load_hidden = [&](const float* src, int lds) {
     if (lds == ldh && (((uintptr_t)src) & 15) == 0) {      // published panel (or a chain whose rows are ldh wide): straight copy
       copy_f4(hs, src, (B * ldh) >> 2);
+      cp_async_wait();
       __syncthreads();
       return;
     }
@@ -218,28 +254,48 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
     __syncthreads();
   };
 
-  for (int step = 0; step < p.n_steps; ++step) {
-    const int* idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
-    const int bit = p.pcd ? (bit0 + step) % V : 0;
-    // ---- the whole minibatch into vbuf (transposed), the own rows into v0o ----
-    if (tid < BTS) sidx[tid] = tid < B ? (idxp ? idxp[tid] : tid) : -1;
-    __syncthreads();
-    for (int i = tid; i < V; i += NT) {
+  // Propdown work items: (row, part of its column quads) — a whole row per warp when the CTA owns >= 5 rows, else the row
+  // split over 2 or 4 warps.  A lane holds quads lane + 32 t of its part.  The first item of every warp goes into registers
+  // ahead of the grid barrier in front of a propdown (W does not change between the statistics passes).
+  const int NTQ = (p.CQ + 31) >> 5;                                 // 32-quad blocks in a row
+  const int SPLIT = nr > 4 ? 1 : nr > 2 ? 2 : 4, TPS = (NTQ + SPLIT - 1) / SPLIT, nitem = nr * SPLIT;
+  float* part = red;                                               // [nitem][BTS] partial dot products
+  auto load_item = [&](int it, float4 (&w)[8]) {
+    if (it < nitem) {
+      const int r = it / SPLIT, t0 = (it - r * SPLIT) * TPS;
+      const float* wr = p.W + (size_t)(i0 + r) * ldw;
 #pragma unroll
-      for (int b0 = 0; b0 < MAXB; b0 += 4) {
-        if (b0 < BTS) {
-          const long long r0 = sidx[b0], r1 = sidx[b0 + 1], r2 = sidx[b0 + 2], r3 = sidx[b0 + 3];
-          float4 x;
-          x.x = r0 >= 0 ? __ldg(&p.data[r0 * p.ld_data + i]) : 0.f;
-          x.y = r1 >= 0 ? __ldg(&p.data[r1 * p.ld_data + i]) : 0.f;
-          x.z = r2 >= 0 ? __ldg(&p.data[r2 * p.ld_data + i]) : 0.f;
-          x.w = r3 >= 0 ? __ldg(&p.data[r3 * p.ld_data + i]) : 0.f;
-          *reinterpret_cast<float4*>(vbuf + i * BTS + b0) = x;
-        }
+      for (int t = 0; t < 8; ++t) {
+        const int q = lane + 32 * (t0 + t);
+        w[t] = (t < TPS && q < p.CQ) ? __ldcg(reinterpret_cast<const float4*>(wr + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  };
+  float4 wreg[8];
+  float vb_pre = 0.f;                                              // visible bias of this thread's first propdown output
+
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int bit = p.pcd ? (bit0 + step) % V : 0;
+    // ---- the minibatch (published slice by slice before the barrier that ended the previous step) and the own column
+    //      quads of W into shared memory ----
+    if (step == 0) {
+      gather_slice(0);
+      mark();   // own rows of the minibatch published
+      grid_sync(p.bar, bar_target);
+      mark();
+    }
+    if (p.wcol_cached) {
+      for (int qq = 0; qq < nq; ++qq) {
+        const float* wp = p.W + 4 * (q0 + qq);
+        float4* wq = wcol + (size_t)qq * V;
+#pragma unroll 4
+        for (int i = tid; i < V; i += NT) cp_async16(wq + i, wp + (size_t)i * ldw);
+      }
+    }
+    copy_f4(vbuf, p.Vg, (V * BTS) >> 2);
+    if (tid < nq * 4) hbo[tid] = 4 * q0 + tid < H ? __ldcg(&p.hb[4 * q0 + tid]) : 0.f;
+    cp_async_wait();
     __syncthreads();
-    for (int e = tid; e < nr * BTS; e += NT) v0o[e] = vbuf[i0 * BTS + e];
 
     mark();   // gathered
     // =============================== positive phase (own columns) ===============================
@@ -250,7 +306,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
         const int qq = e / (BTS * 4), b = (e >> 2) % BTS, c = e & 3, j = 4 * (q0 + qq) + c;
         float mean = 0.f, smp = 0.f;      // padding rows / columns of the published panels are written as zeros
         if (b < B && j < H) {
-          mean = sigmoid_fast_(preo[e] + __ldcg(&p.hb[j]));
+          mean = sigmoid_fast_(preo[e] + hbo[qq * 4 + c]);
           if (!p.pcd) smp = rng_uniform(rs0, (long long)b * H + j) < mean ? 1.f : 0.f;
         }
         __stcg(&p.PHg[b * ldh + j], mean);
@@ -270,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
         for (int qq = 0; qq < nq; ++qq) {
           const int j = 4 * (q0 + qq) + pc;
           if (j < H) {
-            const float pre = preo[(qq * BTS + pb) * 4 + pc] + __ldcg(&p.hb[j]);
+            const float pre = preo[(qq * BTS + pb) * 4 + pc] + hbo[qq * 4 + pc];
             h0 += softplusf_(pre);
             h1 += softplusf_(pre + d * __ldcg(&p.W[(size_t)bit * ldw + j]));
           }
@@ -285,6 +341,8 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       }
     }
     mark();   // positive phase done
+    load_item(warp, wreg);
+    if (tid < nr * BTS) vb_pre = __ldcg(&p.vb[i0 + tid / BTS]);
     grid_sync(p.bar, bar_target);
     mark();
     if (p.pcd && cta == 0 && warp == 0) {
@@ -316,63 +374,64 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       // chain state: CD starts from the fresh sample, PCD from the persistent chain (src/rbm.py:308-311)
       if (p.pcd && s == 0) load_hidden(p.P, H);
       else load_hidden(p.Hg, ldh);
-      // ---- propdown of the own rows: one warp per row, lanes over the column quads ----
-      for (int r = warp; r < nr; r += NWARP) {
-        const int i = i0 + r;
-        float acc[MAXB];
+      mark();   // hidden panel
+      // ---- propdown of the own rows: the lanes of a warp sum their quads of W against the hidden panel for every
+      //      minibatch row and are joined by ONE transposing reduction per item; split rows meet in shared memory ----
+      for (int it = warp; it < nitem; it += NWARP) {
+        const int t0 = (it % SPLIT) * TPS;
+        float4 wnext[8];
+        load_item(it + NWARP, wnext);
+        float acc[32];
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
-        const float* wr = p.W + (size_t)i * ldw;
-        float4 wreg[8];                                          // ldw <= 1024: all loads of the row in flight at once
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int q = lane + 32 * t;
-          wreg[t] = q < p.CQ ? __ldcg(reinterpret_cast<const float4*>(wr + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float vb_i = __ldcg(&p.vb[i]);
+        for (int b = 0; b < 32; ++b) acc[b] = 0.f;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const int q = lane + 32 * t;
-          if (q < p.CQ) {
+          const int q = lane + 32 * (t0 + t);
+          if (t < TPS && 32 * (t0 + t) < p.CQ) {                     // (warp-uniform)
             const float4 w = wreg[t];
+            const float* hp = hs + 4 * (q < p.CQ ? q : 0);         // (w is zero beyond the last quad)
 #pragma unroll
-            for (int b = 0; b < MAXB; ++b) {
-              if (b < BTS) {
-                const float4 h4 = *reinterpret_cast<const float4*>(hs + b * ldh + 4 * q);
-                acc[b] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, acc[b]))));
-              }
-            }
-          }
-        }
-        float mine = 0.f;
+            for (int bh = 0; bh < MAXB; bh += MAXB / 2) {          // ten loads in flight
+              float4 h[MAXB / 2];
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b) {
-          if (b < BTS) {
-            const float t = warp_sum(acc[b]);
-            if (lane == b) mine = t;
-          }
-        }
-        if (lane < BTS) {
-          const int b = lane;
-          float v_in = 0.f, mean = 0.f;
-          if (b < B) {
-            const float pre = mine + vb_i;
-            if (p.kind == MDBN_GRBM) {
-              mean = pre;
-              v_in = pre;                                        // mean-field visible (src/rbm.py:669)
-            } else {
-              mean = sigmoidf_(pre);
-              v_in = rng_uniform(rs_v, (long long)b * V + i) < mean ? 1.f : 0.f;
-            }
-            if (last && !p.pcd) {
-              const float t0 = v0o[r * BTS + b];
-              if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t0; cost_acc += d * d; }      // :697
-              else cost_acc += t0 * softplusf_(-pre) + (1.f - t0) * softplusf_(pre);                    // :479-480
+              for (int b = 0; b < MAXB / 2; ++b)
+                if (bh + b < BTS) h[b] = *reinterpret_cast<const float4*>(hp + (bh + b) * ldh);
+#pragma unroll
+              for (int b = 0; b < MAXB / 2; ++b)
+                if (bh + b < BTS)
+                  acc[bh + b] = fmaf(h[b].x, w.x, fmaf(h[b].y, w.y, fmaf(h[b].z, w.z, fmaf(h[b].w, w.w, acc[bh + b]))));
             }
           }
-          __stcg(&p.Vg[(size_t)i * BTS + b], v_in);
-          if (last) nvo[r * BTS + b] = mean;
         }
+        const float tot = warp_transpose_sum(acc, lane);
+        if (lane < BTS) part[it * BTS + lane] = tot;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) wreg[t] = wnext[t];
+      }
+      __syncthreads();
+      for (int e = tid; e < nr * BTS; e += NT) {
+        const int r = e / BTS, b = e - r * BTS, i = i0 + r;
+        float v_in = 0.f, mean = 0.f;
+        if (b < B) {
+          float pre = 0.f;
+          for (int sp = 0; sp < SPLIT; ++sp) pre += part[(r * SPLIT + sp) * BTS + b];
+          pre += e == tid ? vb_pre : __ldcg(&p.vb[i]);
+          if (p.kind == MDBN_GRBM) {
+            mean = pre;
+            v_in = pre;                                        // mean-field visible (src/rbm.py:669)
+          } else {
+            mean = sigmoidf_(pre);
+            v_in = rng_uniform(rs_v, (long long)b * V + i) < mean ? 1.f : 0.f;
+          }
+          if (last && !p.pcd) {
+            const float t0 = v0o[e];
+            if (p.kind == MDBN_GRBM) { const float d = sigmoidf_(pre) - t0; cost_acc += d * d; }      // :697
+            // cross entropy t0 softplus(-pre) + (1 - t0) softplus(pre) (:479-480), with softplus(-x) = softplus(x) - x
+            else cost_acc += softplusf_(pre) - t0 * pre;
+          }
+        }
+        __stcg(&p.Vg[(size_t)i0 * BTS + e], v_in);
+        if (last) nvo[e] = mean;
       }
       mark();   // hidden panel + propdown
       if (last && !p.pcd) {
@@ -383,14 +442,16 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       mark();
       // ---- the whole visible state, then the hidden units of the own columns ----
       copy_f4(vbuf, p.Vg, (V * BTS) >> 2);
+      cp_async_wait();
       __syncthreads();
+      mark();   // visible panel
       propup(false);
       for (int e = tid; e < nq * BTS * 4; e += NT) {
         const int qq = e / (BTS * 4), b = (e >> 2) % BTS, c = e & 3, j = 4 * (q0 + qq) + c;
         float mean = 0.f, smp = 0.f;
         const bool real = b < B && j < H;
         if (real) {
-          mean = sigmoid_fast_(preo[e] + __ldcg(&p.hb[j]));
+          mean = sigmoid_fast_(preo[e] + hbo[qq * 4 + c]);
           smp = rng_uniform(rs_h, (long long)b * H + j) < mean ? 1.f : 0.f;
         }
         if (!last) __stcg(&p.Hg[b * ldh + j], smp);
@@ -401,6 +462,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
         }
       }
       mark();   // visible panel + propup
+      if (!last) load_item(warp, wreg);
       grid_sync(p.bar, bar_target);
       mark();
     }
@@ -418,71 +480,119 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       const int ncq = min(p.HC, ldh - c0) >> 2;          // quads in this chunk
       float* phc = vbuf;
       float* nhc = vbuf + BTS * p.HC;
+      const int groups = ncq <= 128 ? 2 : 1;             // narrow chunks: two rows in flight
+      const int qd = tid % (NT / groups), rg = tid / (NT / groups);
+      const int j0 = c0 + 4 * qd;
+      const bool active = qd < ncq;
+      // A thread takes RB rows at a time for its column quad: the W / W_speed / snapshot quads of the first block (all the
+      // rows of a thread up to V = 1184) are requested ahead of the panel copy; the hidden means of a minibatch row are read once
+      // for the RB rows, v0 / nv of a row as quads over the minibatch
+      constexpr int RB = 4;
+      float4 w4[RB], s4[RB], n4[RB];
+      auto load_block = [&](int m0, float4 (&w)[RB], float4 (&sp)[RB], float4 (&n)[RB]) {
+#pragma unroll
+        for (int m = 0; m < RB; ++m) {
+          const int r = rg + groups * (m0 + m);
+          n[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (active && r < nr) {
+            const size_t o = (size_t)(i0 + r) * ldw + j0;
+            w[m] = __ldcg(reinterpret_cast<const float4*>(p.W + o));
+            sp[m] = __ldcg(reinterpret_cast<const float4*>(p.S + o));
+            if (p.Wsnap) n[m] = __ldcg(reinterpret_cast<const float4*>(p.Wsnap + o));
+          }
+        }
+      };
+      load_block(0, w4, s4, n4);
       __syncthreads();
       if (p.HC == ldh) {            // one chunk: the panels are contiguous
         copy_f4(phc, p.PHg, (BTS * ldh) >> 2);
         copy_f4(nhc, p.NHg, (BTS * ldh) >> 2);
       } else {
         for (int e = tid; e < BTS * ncq; e += NT) {
-          const int b = e / ncq, qd = e - b * ncq;
-          reinterpret_cast<float4*>(phc + b * p.HC)[qd] = __ldcg(reinterpret_cast<const float4*>(p.PHg + b * ldh + c0) + qd);
-          reinterpret_cast<float4*>(nhc + b * p.HC)[qd] = __ldcg(reinterpret_cast<const float4*>(p.NHg + b * ldh + c0) + qd);
+          const int b = e / ncq, qe = e - b * ncq;
+          cp_async16(reinterpret_cast<float4*>(phc + b * p.HC) + qe, reinterpret_cast<const float4*>(p.PHg + b * ldh + c0) + qe);
+          cp_async16(reinterpret_cast<float4*>(nhc + b * p.HC) + qe, reinterpret_cast<const float4*>(p.NHg + b * ldh + c0) + qe);
         }
       }
+      if (c0 == 0) {
+        // under the panel copy (different warps, so that their L2 round trips overlap): visible bias of the own rows (src/rbm.py:417), hidden bias of the own columns (:416)
+        for (int r = tid; r < nr; r += NT) {
+          float gs = 0.f;
+          for (int b = 0; b < B; ++b) gs += v0o[r * BTS + b] - nvo[r * BTS + b];
+          const float gb = gs * p.inv_b, sv = __ldcg(&p.Svb[i0 + r]);
+          p.Svb[i0 + r] = gb + (sv - gb) * p.u.mom;
+          p.vb[i0 + r] = __ldcg(&p.vb[i0 + r]) + sv * p.u.lr;
+        }
+        for (int e = tid - NT / 2; e >= 0 && e < nq * 4; e += NT) {      // (nq <= 4)
+          const int qq = e >> 2, c = e & 3, j = 4 * (q0 + qq) + c;
+          if (j < H) {
+            float gs = 0.f;
+            for (int b = 0; b < B; ++b) gs += pho[(qq * BTS + b) * 4 + c] - nho[(qq * BTS + b) * 4 + c];
+            const float gb = gs * p.inv_b, sv = __ldcg(&p.Shb[j]);
+            p.Shb[j] = gb + (sv - gb) * p.u.mom;
+            p.hb[j] = __ldcg(&p.hb[j]) + sv * p.u.lr;
+          }
+        }
+      }
+      cp_async_wait();
       __syncthreads();
-      const int groups = ncq <= 128 ? 2 : 1;             // narrow chunks: two rows in flight
-      const int qd = tid % (NT / groups), rg = tid / (NT / groups);
-      if (qd < ncq) {
-        const int j0 = c0 + 4 * qd;
-        for (int r = rg; r < nr; r += groups) {
-          const size_t o = (size_t)(i0 + r) * ldw + j0;
-          const float4 w4 = __ldcg(reinterpret_cast<const float4*>(p.W + o)), s4 = __ldcg(reinterpret_cast<const float4*>(p.S + o));
-          const float4 n4 = p.Wsnap ? __ldcg(reinterpret_cast<const float4*>(p.Wsnap + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float g4[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int b = 0; b < B; ++b) {
-            const float a = v0o[r * BTS + b], n = nvo[r * BTS + b];
-            const float4 ph4 = *reinterpret_cast<const float4*>(phc + b * p.HC + 4 * qd);
-            const float4 nh4 = *reinterpret_cast<const float4*>(nhc + b * p.HC + 4 * qd);
-            g4[0] = fmaf(a, ph4.x, g4[0]); g4[0] = fmaf(-n, nh4.x, g4[0]);
-            g4[1] = fmaf(a, ph4.y, g4[1]); g4[1] = fmaf(-n, nh4.y, g4[1]);
-            g4[2] = fmaf(a, ph4.z, g4[2]); g4[2] = fmaf(-n, nh4.z, g4[2]);
-            g4[3] = fmaf(a, ph4.w, g4[3]); g4[3] = fmaf(-n, nh4.w, g4[3]);
-          }
-          {
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, nv[4] = {n4.x, n4.y, n4.z, n4.w};
-            float wo[4], so[4];
+      mark();   // mean panels
+      if (active) {
+        for (int m0 = 0; rg + groups * m0 < nr; m0 += RB) {
+          if (m0 > 0) load_block(m0, w4, s4, n4);
+          float g[RB][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              wo[c] = wv[c]; so[c] = sv[c];
-              if (j0 + c < H) update_one(p.u, g4[c], wv[c], sv[c], nv[c], p.Wsnap != nullptr, wo[c], so[c]);
+          for (int m = 0; m < RB; ++m) g[m][0] = g[m][1] = g[m][2] = g[m][3] = 0.f;
+          for (int b0 = 0; b0 < BTS; b0 += 4) {      // (rows b >= B of every panel are zeros)
+            float av[RB][4], nv[RB][4];
+#pragma unroll
+            for (int m = 0; m < RB; ++m) {
+              const int r = min(rg + groups * (m0 + m), nr - 1);
+              const float4 a4 = *reinterpret_cast<const float4*>(v0o + r * BTS + b0);
+              const float4 m4 = *reinterpret_cast<const float4*>(nvo + r * BTS + b0);
+              av[m][0] = a4.x; av[m][1] = a4.y; av[m][2] = a4.z; av[m][3] = a4.w;
+              nv[m][0] = m4.x; nv[m][1] = m4.y; nv[m][2] = m4.z; nv[m][3] = m4.w;
             }
-            *reinterpret_cast<float4*>(p.W + o) = make_float4(wo[0], wo[1], wo[2], wo[3]);
-            *reinterpret_cast<float4*>(p.S + o) = make_float4(so[0], so[1], so[2], so[3]);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+              const float4 ph4 = *reinterpret_cast<const float4*>(phc + (b0 + bb) * p.HC + 4 * qd);
+              const float4 nh4 = *reinterpret_cast<const float4*>(nhc + (b0 + bb) * p.HC + 4 * qd);
+#pragma unroll
+              for (int m = 0; m < RB; ++m) {
+                g[m][0] = fmaf(av[m][bb], ph4.x, g[m][0]); g[m][0] = fmaf(-nv[m][bb], nh4.x, g[m][0]);
+                g[m][1] = fmaf(av[m][bb], ph4.y, g[m][1]); g[m][1] = fmaf(-nv[m][bb], nh4.y, g[m][1]);
+                g[m][2] = fmaf(av[m][bb], ph4.z, g[m][2]); g[m][2] = fmaf(-nv[m][bb], nh4.z, g[m][2]);
+                g[m][3] = fmaf(av[m][bb], ph4.w, g[m][3]); g[m][3] = fmaf(-nv[m][bb], nh4.w, g[m][3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < RB; ++m) {
+            const int r = rg + groups * (m0 + m);
+            if (r < nr) {
+              const size_t o = (size_t)(i0 + r) * ldw + j0;
+              const float wv[4] = {w4[m].x, w4[m].y, w4[m].z, w4[m].w}, sv[4] = {s4[m].x, s4[m].y, s4[m].z, s4[m].w};
+              const float sn4[4] = {n4[m].x, n4[m].y, n4[m].z, n4[m].w};
+              float wo[4], so[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                wo[c] = wv[c]; so[c] = sv[c];
+                if (j0 + c < H) update_one(p.u, g[m][c], wv[c], sv[c], sn4[c], p.Wsnap != nullptr, wo[c], so[c]);
+              }
+              *reinterpret_cast<float4*>(p.W + o) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+              *reinterpret_cast<float4*>(p.S + o) = make_float4(so[0], so[1], so[2], so[3]);
+            }
           }
         }
-      }
-    }
-    // visible bias of the own rows (src/rbm.py:417), hidden bias of the own columns (:416)
-    for (int r = tid; r < nr; r += NT) {
-      float gs = 0.f;
-      for (int b = 0; b < B; ++b) gs += v0o[r * BTS + b] - nvo[r * BTS + b];
-      const float gb = gs * p.inv_b, sv = __ldcg(&p.Svb[i0 + r]);
-      p.Svb[i0 + r] = gb + (sv - gb) * p.u.mom;
-      p.vb[i0 + r] = __ldcg(&p.vb[i0 + r]) + sv * p.u.lr;
-    }
-    for (int e = tid; e < nq * 4; e += NT) {
-      const int qq = e >> 2, c = e & 3, j = 4 * (q0 + qq) + c;
-      if (j < H) {
-        float gs = 0.f;
-        for (int b = 0; b < B; ++b) gs += pho[(qq * BTS + b) * 4 + c] - nho[(qq * BTS + b) * 4 + c];
-        const float gb = gs * p.inv_b, sv = __ldcg(&p.Shb[j]);
-        p.Shb[j] = gb + (sv - gb) * p.u.mom;
-        p.hb[j] = __ldcg(&p.hb[j]) + sv * p.u.lr;
       }
     }
     mark();   // statistics + update done
     // the next step of a chained launch reads columns of W that other CTAs have just written, and overwrites the panels
-    if (step + 1 < p.n_steps) grid_sync(p.bar, bar_target);
+    if (step + 1 < p.n_steps) {
+      __syncthreads();                 // v0o is dead (bias update done)
+      gather_slice(step + 1);
+      grid_sync(p.bar, bar_target);
+    }
   }
   if (p.pcd && cta == 0 && tid == 0) *p.bit_idx = (bit0 + p.n_steps) % V;     // src/rbm.py:445
 
@@ -500,7 +610,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
 }
 
 struct Geometry {
-  int BTS, CQ, ldh, NQ, NR, HC, grid;
+  int BTS, CQ, ldh, NQ, NR, HC, grid, wcol_cached;
   int off_vbuf, off_hs, off_v0o, off_nvo, off_red, off_preo, off_pho, off_nho, off_misc, off_wcol;
   size_t smem;
   bool ok;
@@ -527,14 +637,19 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   g.off_hs = take((size_t)g.BTS * g.ldh * 4);
   g.off_v0o = take((size_t)g.NR * g.BTS * 4);
   g.off_nvo = take((size_t)g.NR * g.BTS * 4);
-  g.off_red = take((size_t)NT * 16 * 4 + 3 * MAXB * 4 * 4);
+  const size_t red_up = (size_t)NT * 16 * 4 + 3 * MAXB * 4 * 4;                      // propup partials
+  const size_t red_down = (size_t)(g.NR > 4 ? g.NR : 4 * g.NR) * g.BTS * 4;           // propdown partials
+  g.off_red = take(red_up > red_down ? red_up : red_down);
   g.off_preo = take((size_t)g.NQ * g.BTS * 16);
   g.off_pho = take((size_t)g.NQ * g.BTS * 16);
   g.off_nho = take((size_t)g.NQ * g.BTS * 16);
   g.off_misc = take(512);
-  g.off_wcol = take((size_t)a.V * 16);
+  // all own column quads where they fit (they are then fetched once per step), else one quad restaged per propagation
+  const size_t fixed = off;
+  g.wcol_cached = fixed + (size_t)g.NQ * a.V * 16 <= MAX_SMEM ? 1 : 0;
+  g.off_wcol = take((size_t)(g.wcol_cached ? g.NQ : 1) * a.V * 16);
   g.smem = off;
-  g.ok = g.smem <= 200 * 1024;
+  g.ok = g.smem <= MAX_SMEM;
   return g;
 }
 
@@ -566,6 +681,7 @@ int mid_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t s
   p.c2 = (uint32_t)a.rng.offset; p.c3 = (uint32_t)(a.rng.offset >> 32);
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
+  p.wcol_cached = g.wcol_cached;
   p.BTS = g.BTS; p.CQ = g.CQ; p.ldh = g.ldh; p.NQ = g.NQ; p.NR = g.NR; p.HC = g.HC;
   p.off_vbuf = g.off_vbuf; p.off_hs = g.off_hs; p.off_v0o = g.off_v0o; p.off_nvo = g.off_nvo; p.off_red = g.off_red;
   p.off_preo = g.off_preo; p.off_pho = g.off_pho; p.off_nho = g.off_nho; p.off_misc = g.off_misc; p.off_wcol = g.off_wcol;
@@ -582,7 +698,7 @@ int mid_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t s
   p.dbg = want_timing ? reinterpret_cast<unsigned long long*>(c->barrier) + 64 : nullptr;
   static bool configured[64] = {};
   if (!configured[c->device]) {
-    MDBN_CUDA(cudaFuncSetAttribute(md::cd_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MDBN_CUDA(cudaFuncSetAttribute(md::cd_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)md::MAX_SMEM));
     configured[c->device] = true;
   }
   void* args[] = {(void*)&p};
@@ -593,7 +709,9 @@ int mid_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t s
     MDBN_CUDA(cudaStreamSynchronize(st));
     MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[mid timeline us] V=%d H=%d B=%d k=%d grid=%d NQ=%d NR=%d:", a.V, a.H, a.B, a.k, g.grid, g.NQ, g.NR);
-    for (int i = 1; i < 12; ++i) fprintf(stderr, " %.1f", (double)((long long)(t[i] - t[0])) * 1e-3);
+    // own minibatch rows published, barrier, minibatch + W columns in place, positive, barrier, hidden panel, propdown,
+    // barrier, visible panel, propup, barrier, mean panels, statistics  (k = 1, one statistics chunk)
+    for (int i = 1; i < 14 && t[i] >= t[0]; ++i) fprintf(stderr, " %.1f", (double)((long long)(t[i] - t[0])) * 1e-3);
     fprintf(stderr, "\n");
   }
   return 0;
