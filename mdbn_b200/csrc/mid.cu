@@ -75,6 +75,12 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ float4 lds128v(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
 // Sum over the 32 lanes of v[0..MAXB) at once: lane L returns the warp total of v[L] (0 for L >= MAXB).  31 shuffles in
 // five levels instead of 5 per value; fixed order.
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
@@ -272,6 +278,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
     }
   };
   float4 wreg[8];
+  const uint32_t hs_u32 = (uint32_t)__cvta_generic_to_shared(hs);
   float vb_pre = 0.f;                                              // visible bias of this thread's first propdown output
 
   for (int step = 0; step < p.n_steps; ++step) {
@@ -379,8 +386,7 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       //      minibatch row and are joined by ONE transposing reduction per item; split rows meet in shared memory ----
       for (int it = warp; it < nitem; it += NWARP) {
         const int t0 = (it % SPLIT) * TPS;
-        float4 wnext[8];
-        load_item(it + NWARP, wnext);
+        if (it != warp) load_item(it, wreg);                       // (only CTAs with more than 8 rows: V > 1184)
         float acc[32];
 #pragma unroll
         for (int b = 0; b < 32; ++b) acc[b] = 0.f;
@@ -389,13 +395,13 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
           const int q = lane + 32 * (t0 + t);
           if (t < TPS && 32 * (t0 + t) < p.CQ) {                     // (warp-uniform)
             const float4 w = wreg[t];
-            const float* hp = hs + 4 * (q < p.CQ ? q : 0);         // (w is zero beyond the last quad)
+            const uint32_t ha = hs_u32 + 16u * (uint32_t)(q < p.CQ ? q : 0);      // (w is zero beyond the last quad)
 #pragma unroll
-            for (int bh = 0; bh < MAXB; bh += MAXB / 2) {          // ten loads in flight
+            for (int bh = 0; bh < MAXB; bh += MAXB / 2) {          // ten loads in flight (volatile: issued back to back)
               float4 h[MAXB / 2];
 #pragma unroll
               for (int b = 0; b < MAXB / 2; ++b)
-                if (bh + b < BTS) h[b] = *reinterpret_cast<const float4*>(hp + (bh + b) * ldh);
+                if (bh + b < BTS) h[b] = lds128v(ha + (uint32_t)((bh + b) * ldh) * 4u);
 #pragma unroll
               for (int b = 0; b < MAXB / 2; ++b)
                 if (bh + b < BTS)
@@ -405,9 +411,8 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
         }
         const float tot = warp_transpose_sum(acc, lane);
         if (lane < BTS) part[it * BTS + lane] = tot;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) wreg[t] = wnext[t];
       }
+      mark();   // propdown sums
       __syncthreads();
       for (int e = tid; e < nr * BTS; e += NT) {
         const int r = e / BTS, b = e - r * BTS, i = i0 + r;
@@ -517,20 +522,27 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       if (c0 == 0) {
         // under the panel copy (different warps, so that their L2 round trips overlap): visible bias of the own rows (src/rbm.py:417), hidden bias of the own columns (:416)
         for (int r = tid; r < nr; r += NT) {
+          const float sv = __ldcg(&p.Svb[i0 + r]), vbo = __ldcg(&p.vb[i0 + r]);
           float gs = 0.f;
-          for (int b = 0; b < B; ++b) gs += v0o[r * BTS + b] - nvo[r * BTS + b];
-          const float gb = gs * p.inv_b, sv = __ldcg(&p.Svb[i0 + r]);
+          for (int b0 = 0; b0 < BTS; b0 += 4) {      // (rows b >= B are zeros in both slabs)
+            const float4 a4 = *reinterpret_cast<const float4*>(v0o + r * BTS + b0);
+            const float4 m4 = *reinterpret_cast<const float4*>(nvo + r * BTS + b0);
+            gs += ((a4.x - m4.x) + (a4.y - m4.y)) + ((a4.z - m4.z) + (a4.w - m4.w));
+          }
+          const float gb = gs * p.inv_b;
           p.Svb[i0 + r] = gb + (sv - gb) * p.u.mom;
-          p.vb[i0 + r] = __ldcg(&p.vb[i0 + r]) + sv * p.u.lr;
+          p.vb[i0 + r] = vbo + sv * p.u.lr;
         }
         for (int e = tid - NT / 2; e >= 0 && e < nq * 4; e += NT) {      // (nq <= 4)
           const int qq = e >> 2, c = e & 3, j = 4 * (q0 + qq) + c;
           if (j < H) {
+            const float sv = __ldcg(&p.Shb[j]);
             float gs = 0.f;
+#pragma unroll 4
             for (int b = 0; b < B; ++b) gs += pho[(qq * BTS + b) * 4 + c] - nho[(qq * BTS + b) * 4 + c];
-            const float gb = gs * p.inv_b, sv = __ldcg(&p.Shb[j]);
+            const float gb = gs * p.inv_b;
             p.Shb[j] = gb + (sv - gb) * p.u.mom;
-            p.hb[j] = __ldcg(&p.hb[j]) + sv * p.u.lr;
+            p.hb[j] = hbo[e] + sv * p.u.lr;
           }
         }
       }
@@ -709,9 +721,9 @@ int mid_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t s
     MDBN_CUDA(cudaStreamSynchronize(st));
     MDBN_CUDA(cudaMemcpy(t, p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[mid timeline us] V=%d H=%d B=%d k=%d grid=%d NQ=%d NR=%d:", a.V, a.H, a.B, a.k, g.grid, g.NQ, g.NR);
-    // own minibatch rows published, barrier, minibatch + W columns in place, positive, barrier, hidden panel, propdown,
-    // barrier, visible panel, propup, barrier, mean panels, statistics  (k = 1, one statistics chunk)
-    for (int i = 1; i < 14 && t[i] >= t[0]; ++i) fprintf(stderr, " %.1f", (double)((long long)(t[i] - t[0])) * 1e-3);
+    // own minibatch rows published, barrier, minibatch + W columns in place, positive, barrier, hidden panel, propdown sums,
+    // propdown epilogue, barrier, visible panel, propup, barrier, mean panels, statistics  (k = 1, one statistics chunk)
+    for (int i = 1; i < 15 && t[i] >= t[0]; ++i) fprintf(stderr, " %.1f", (double)((long long)(t[i] - t[0])) * 1e-3);
     fprintf(stderr, "\n");
   }
   return 0;

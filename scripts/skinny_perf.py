@@ -13,6 +13,10 @@ CASES = {
     "ge_b10_pcd5": (M.GRBM, 19937, 400, 10, 5, True, dict(lr=0.005, lambda_1=0.01, lambda_2=0.1)),
     "mnist_b20_cd1": (M.RBM, 784, 500, 20, 1, False, dict(lr=0.1, weightcost=0.0002)),
     "dbn1000_b20_cd1": (M.RBM, 1000, 1000, 20, 1, False, dict(lr=0.01, weightcost=0.0002)),
+    "mnist_b10_cd1": (M.RBM, 784, 500, 10, 1, False, dict(lr=0.1, weightcost=0.0002)),
+    "dbn784x1000_b10_cd1": (M.RBM, 784, 1000, 10, 1, False, dict(lr=0.01, weightcost=0.0002)),
+    "dbn1000_b10_cd1": (M.RBM, 1000, 1000, 10, 1, False, dict(lr=0.01, weightcost=0.0002)),
+    "dbn1000_b10_pcd5": (M.RBM, 1000, 1000, 10, 5, True, dict(lr=0.01, weightcost=0.0002)),
     "sm_b20_cd1": (M.GRBM, 1686, 200, 20, 1, False, dict(lr=0.005, lambda_1=0.01, lambda_2=0.01)),
 }
 names = sys.argv[1:] or ["ge_b10_pcd1", "ge_b20_cd1"]
