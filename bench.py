@@ -520,8 +520,11 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_how": traffic_note,
-                    "kernel": "cd_skinny_kernel" if B <= 20 else "tc_gemm_kernel<SPLIT> (tcgen05, fp32-exact split TF32; "
-                                                                 "statistics GEMM with the update fused in its epilogue)",
+                    # B <= 20: the broadcast kernel where the layer fits it (api.cu mid_wanted: V * ldw <= 4M), else
+                    # the row-slab kernel
+                    "kernel": ("cd_mid_kernel" if V * ((H + 7) // 8 * 8) <= (4 << 20) else "cd_skinny_kernel") if B <= 20 else
+                              "tc_gemm_kernel<SPLIT> (tcgen05, fp32-exact split TF32; statistics GEMM with the update fused "
+                              "in its epilogue)",
                     "peak_source": how,
                     "algorithmic_bytes_per_step": abytes, "steps_per_launch": chain,
                     "algorithmic_bytes_per_launch": abytes * chain}

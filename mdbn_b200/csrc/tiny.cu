@@ -20,6 +20,7 @@ namespace tn {
 
 constexpr int NT = 512;
 constexpr int CL = 8;            // CTAs per cluster (portable maximum)
+constexpr int MH = 20;           // rows of M = W^T W a thread of the register edition of the local Gibbs steps holds
 
 struct Params {
   float *W, *S;
@@ -40,7 +41,7 @@ struct Params {
   long long u_step_stride, u_off_v, u_off_h;
   int rows_per_cta, rows_alloc, BTS, CQ, G, lds;
   int use_m;                 // GRBM with k > 1: Gibbs steps 0..k-2 run on M = W^T W (see below)
-  int off_M, off_Mp;
+  int off_M, off_Mp, off_U;
   unsigned long long* dbg;   // optional phase timeline (MDBN_TINY_TIMING=1), rank 0, first step
   // shared-memory byte offsets
   int off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb,
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
   float* shbs = reinterpret_cast<float*>(smem + p.off_shb);   // [ldw]
   float* Ms = reinterpret_cast<float*>(smem + p.off_M);       // [H+1][ldw]  W^T W of ALL rows; row H = vb . W
   float* Mp = reinterpret_cast<float*>(smem + p.off_Mp);      // [H+1][ldw]  this CTA's share of it
+  float* Us = reinterpret_cast<float*>(smem + p.off_U);       // [k-1][B][CQ][4] uniforms of the local Gibbs steps (use_m == 2)
   float* park = reinterpret_cast<float*>(smem + p.off_park);  // [G][BTS][ldw] row-group partials of a propup
   float* misc = reinterpret_cast<float*>(smem + p.off_misc);  // [64]: block_sum scratch, [40] cost partial, [48..] sidx
 
@@ -335,7 +337,89 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
 
     // =============================== k Gibbs steps ===============================
     float cost_acc = 0.f;
-    for (int s = 0; s < p.k; ++s) {
+    int s_begin = 0;
+    if (p.use_m == 2) {
+      // Register edition of the local steps below (H <= 2 MH): thread = (minibatch row, column quad, half of the rows of
+      // M).  Its 4 x MH block of M = W^T W stays in registers for all k - 1 steps, so a step reads only the chain state
+      // from shared memory (5 LDS.128 instead of 40 LDS.32 + 40 LDS.128 per thread: the loop was bound by the
+      // shared-memory pipe) and the two halves of a dot product are joined with one shuffle.
+      const int pr = tid >> 1, half = tid & 1;
+      const bool mine = pr < B * CQ;
+      const int b = mine ? pr / CQ : 0, q = mine ? pr - b * CQ : 0;
+      const int HH = ((H + 7) >> 3) << 2;                        // rows per half (multiple of 4, <= MH)
+      float4 mreg[MH];
+#pragma unroll
+      for (int i = 0; i < MH; ++i) {
+        const int row = HH * half + i;
+        mreg[i] = (i < HH && row < H) ? *reinterpret_cast<const float4*>(Ms + row * ldw + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);               // (vb W + hb) for the quad, on the first half only
+      if (half == 0) {
+        const float4 c4 = *reinterpret_cast<const float4*>(Ms + H * ldw + 4 * q);
+        const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * q);
+        a0 = make_float4(c4.x + hb4.x, c4.y + hb4.y, c4.z + hb4.z, c4.w + hb4.w);
+      }
+      // the uniforms of all k - 1 steps first, every Philox block once, spread over the whole CTA (inside the loop every
+      // warp would recompute them step after step: the loop was issue-bound on them)
+      {
+        const int nbq = B * CQ, lanes = NT / nbq;                 // threads per (row, quad): they take the steps round-robin
+        const int e = tid % nbq, s0 = tid / nbq, ub = e / CQ, uq = e - ub * CQ;
+        if (s0 < lanes) {
+#pragma unroll 2
+          for (int s = s0; s < p.k - 1; s += lanes) {
+            const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
+            const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
+            float u[4];
+            if (rs_h.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
+              const long long e0 = (long long)ub * H + 4 * uq;
+              const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs_h.c1, rs_h.c2, rs_h.c3, rs_h.k0, rs_h.k1);
+              u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) u[t] = 4 * uq + t < H ? rng_uniform(rs_h, (long long)ub * H + 4 * uq + t) : 2.f;
+            }
+            *reinterpret_cast<float4*>(Us + ((size_t)s * nbq + e) * 4) = make_float4(u[0], u[1], u[2], u[3]);
+          }
+        }
+      }
+      // chunk offsets of this half's part of the chain state (a chunk beyond the half, or beyond the row, re-reads
+      // chunk 0 against zero rows of M: no branches in the loop)
+      int hoff[MH / 4];
+#pragma unroll
+      for (int i4 = 0; i4 < MH / 4; ++i4) hoff[i4] = (4 * i4 < HH && HH * half + 4 * i4 < ldw) ? 4 * i4 : 0;
+      const float* hrow = hs + b * ldw + HH * half;
+      const float4* up = reinterpret_cast<const float4*>(Us) + (mine ? pr : 0);
+      __syncthreads();
+      mark();   // uniforms of the local steps ready
+      for (int s = 0; s < p.k - 1; ++s) {
+        float4 a = a0;
+#pragma unroll
+        for (int i4 = 0; i4 < MH / 4; ++i4) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hrow + hoff[i4]);
+          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4 m4 = mreg[4 * i4 + t];
+            a.x = fmaf(hv[t], m4.x, a.x); a.y = fmaf(hv[t], m4.y, a.y); a.z = fmaf(hv[t], m4.z, a.z); a.w = fmaf(hv[t], m4.w, a.w);
+          }
+        }
+        const float4 u4 = up[(size_t)s * B * CQ];
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, 1); a.y += __shfl_xor_sync(0xffffffffu, a.y, 1);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, 1); a.w += __shfl_xor_sync(0xffffffffu, a.w, 1);
+        float4 smp;
+        smp.x = (4 * q + 0 < H && u4.x < sigmoid_fast_(a.x)) ? 1.f : 0.f;
+        smp.y = (4 * q + 1 < H && u4.y < sigmoid_fast_(a.y)) ? 1.f : 0.f;
+        smp.z = (4 * q + 2 < H && u4.z < sigmoid_fast_(a.z)) ? 1.f : 0.f;
+        smp.w = (4 * q + 3 < H && u4.w < sigmoid_fast_(a.w)) ? 1.f : 0.f;
+        __syncthreads();
+        if (mine && half == 0) *reinterpret_cast<float4*>(hs + b * ldw + 4 * q) = smp;
+        __syncthreads();
+        if (s == 0) mark();   // first local step
+      }
+      s_begin = p.k - 1;
+      mark();   // local Gibbs steps done
+    }
+    for (int s = s_begin; s < p.k; ++s) {
       const bool last = (s == p.k - 1);
       const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
       const RngSeg rs_v = seg(ubase + p.u_off_v, 1u + 2u * s, step);
@@ -518,7 +602,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
 
 struct Geometry {
   int BTS, CQ, rows_per_cta, rows_alloc, G, lds, use_m;
-  int off_M, off_Mp, off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
+  int off_U, off_M, off_Mp, off_park, off_W, off_S, off_v0, off_nv, off_vin, off_hs, off_pc, off_ph, off_nh, off_part, off_vb, off_svb, off_hb, off_shb,
       off_misc;
   size_t smem;
   bool ok;
@@ -542,6 +626,8 @@ static Geometry plan(const mdbn_cd_args& a) {
   g.G = g.G < 1 ? 1 : (g.G > 8 ? 8 : g.G);
   while (g.G > 1 && (size_t)g.G * hid > 48 * 1024) --g.G;
   g.use_m = a.kind == MDBN_GRBM && a.k > 1 && a.ldw <= 64 && a.B * g.CQ <= NT;
+  static const bool no_mreg = getenv("MDBN_TINY_NO_MREG") != nullptr;
+  if (g.use_m && a.ldw <= 2 * tn::MH && 2 * a.B * g.CQ <= NT && !no_mreg) g.use_m = 2;      // M in registers
   g.off_M = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
   g.off_Mp = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
   g.off_park = take(g.G > 1 ? (size_t)g.G * hid : 0);
@@ -552,6 +638,12 @@ static Geometry plan(const mdbn_cd_args& a) {
   g.off_vb = take((size_t)g.rows_alloc * 4); g.off_svb = take((size_t)g.rows_alloc * 4);
   g.off_hb = take((size_t)a.ldw * 4); g.off_shb = take((size_t)a.ldw * 4);
   g.off_misc = take(512);
+  g.off_U = 0;
+  if (g.use_m == 2) {      // uniforms of the k - 1 local Gibbs steps, [k-1][B][CQ] quads
+    const size_t ub = (size_t)(a.k - 1) * a.B * g.CQ * 16;
+    if (off + ub <= 200 * 1024) g.off_U = take(ub);
+    else g.use_m = 1;
+  }
   g.smem = off;
   g.ok = g.smem <= 200 * 1024;
   return g;
@@ -590,7 +682,7 @@ int tiny_cd_steps(mdbn_ctx* c, const mdbn_cd_args& a, int n_steps, cudaStream_t 
   ULayout ul = u_layout(a.kind, a.noisy, a.B, a.V, a.H);
   p.u_step_stride = ul.step_stride; p.u_off_v = ul.off_v; p.u_off_h = ul.off_h;
   p.rows_per_cta = g.rows_per_cta; p.rows_alloc = g.rows_alloc; p.BTS = g.BTS; p.CQ = g.CQ; p.G = g.G; p.lds = g.lds;
-  p.use_m = g.use_m; p.off_M = g.off_M; p.off_Mp = g.off_Mp;
+  p.use_m = g.use_m; p.off_M = g.off_M; p.off_Mp = g.off_Mp; p.off_U = g.off_U;
   p.off_park = g.off_park;
   p.off_W = g.off_W; p.off_S = g.off_S; p.off_v0 = g.off_v0; p.off_nv = g.off_nv; p.off_vin = g.off_vin;
   p.off_hs = g.off_hs; p.off_pc = g.off_pc; p.off_ph = g.off_ph; p.off_nh = g.off_nh; p.off_part = g.off_part;
