@@ -352,25 +352,6 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
     if (tid < nr * BTS) vb_pre = __ldcg(&p.vb[i0 + tid / BTS]);
     grid_sync(p.bar, bar_target);
     mark();
-    if (p.pcd && cta == 0 && warp == 0) {
-      // monitor: fixed-order sum of the partials over the CTAs, one lane per minibatch row
-      float cb = 0.f;
-      if (lane < B) {
-        float h0 = 0.f, h1 = 0.f;
-        for (int g = 0; g < G; ++g) {
-          h0 += __ldcg(&p.pl_part[((size_t)g * BTS + lane) * 2]);
-          h1 += __ldcg(&p.pl_part[((size_t)g * BTS + lane) * 2 + 1]);
-        }
-        const float x = roundf(vbuf[bit * BTS + lane]), d = 1.f - 2.f * x, vbv = __ldcg(&p.vb[bit]);
-        float vterm;
-        if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
-        else vterm = d * vbv;
-        cb = -(float)V * softplusf_((h1 - h0) + vterm);
-      }
-      cb = warp_sum(cb);
-      if (lane == 0 && p.cost_out) p.cost_out[step] = cb * p.cost_scale;
-    }
-
     // =============================== k Gibbs steps ===============================
     float cost_acc = 0.f;
     for (int s = 0; s < p.k; ++s) {
@@ -382,6 +363,27 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       if (p.pcd && s == 0) load_hidden(p.P, H);
       else load_hidden(p.Hg, ldh);
       mark();   // hidden panel
+      if (p.pcd && s == 0 && warp == NWARP - 1) {
+        // monitor: minibatch row pl_b on one of the LAST CTAs of the grid (they own no or few hidden columns), on the
+        // warp that has a propdown item only on CTAs with 8 rows or more: the partials of all CTAs, lane-strided and
+        // joined by a butterfly (fixed order); v0 is still in vbuf
+        const int pl_b = G - 1 - cta;
+        if (pl_b < B) {
+          float h0 = 0.f, h1 = 0.f;
+          for (int g = lane; g < G; g += 32) {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(p.pl_part + ((size_t)g * BTS + pl_b) * 2));
+            h0 += t.x; h1 += t.y;
+          }
+          h0 = warp_sum(h0); h1 = warp_sum(h1);
+          if (lane == 0) {
+            const float x = roundf(vbuf[bit * BTS + pl_b]), d = 1.f - 2.f * x, vbv = __ldcg(&p.vb[bit]);
+            float vterm;
+            if (p.kind == MDBN_GRBM) { const float a = x - vbv, c = (1.f - x) - vbv; vterm = 0.5f * (a * a - c * c); }
+            else vterm = d * vbv;
+            __stcg(&p.cost_part[pl_b], -(float)V * softplusf_((h1 - h0) + vterm));
+          }
+        }
+      }
       // ---- propdown of the own rows: the lanes of a warp sum their quads of W against the hidden panel for every
       //      minibatch row and are joined by ONE transposing reduction per item; split rows meet in shared memory ----
       for (int it = warp; it < nitem; it += NWARP) {
@@ -471,9 +473,9 @@ __global__ void __launch_bounds__(NT, 1) cd_mid_kernel(const Params p) {
       grid_sync(p.bar, bar_target);
       mark();
     }
-    if (!p.pcd && cta == 0 && warp == 0) {                       // reconstruction cost: fixed-order sum of the CTA partials
+    if (cta == 0 && warp == 0) {      // reconstruction cost: fixed-order sum of the CTA partials; PCD: of the monitor's rows
       float c = 0.f;
-      for (int g = lane; g < G; g += 32) c += __ldcg(&p.cost_part[g]);
+      for (int g = lane; g < (p.pcd ? B : G); g += 32) c += __ldcg(&p.cost_part[g]);
       c = warp_sum(c);
       if (lane == 0 && p.cost_out) p.cost_out[step] = c * p.cost_scale;
     }

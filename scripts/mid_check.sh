@@ -1,12 +1,9 @@
-# mid kernel: parity tests, phase timeline, us per step against the row-slab kernel on the same layers
+# mid kernel: parity tests, phase timeline, us per step
 set -x
-O=gpurun_out/mid8
+O=gpurun_out/mid9
 mkdir -p $O
-python -m pytest tests/test_gpu_parity.py -x -q -k "mid" 2>&1 | tail -5 > $O/tests.log
+python -m pytest tests/test_gpu_parity.py -x -q -k "mid or auto" 2>&1 | tail -5 > $O/tests.log
 cat $O/tests.log
-python scripts/mid_timeline.py 2>&1 | grep timeline | cut -c1-170 > $O/timeline.txt
-cat $O/timeline.txt
-CASES="mnist_b20_cd1 dbn1000_b20_cd1 sm_b20_cd1 mnist_b10_cd1 dbn1000_b10_pcd5"
-MDBN_PATH=mid python scripts/skinny_perf.py $CASES > $O/perf_mid.txt 2>&1
-
-cat $O/perf_mid.txt $O/perf_skinny.txt | cut -c1-260
+for w in mnist_rbm_cd1_b20 mnist_rbm_pcd1_b20; do python bench.py --workload $w --no-cpu-baseline --no-extras > $O/bench_$w.json 2>/dev/null; python -c "
+import json,sys
+d=json.loads(open('$O/bench_$w.json').read().strip().splitlines()[-1]); print('$w', d['ms_per_step'], d['roofline']['frac'], d['roofline'].get('single_launch',{}).get('ms_per_step'))"; done
