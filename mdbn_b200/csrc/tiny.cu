@@ -343,9 +343,15 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       // M).  Its 4 x MH block of M = W^T W stays in registers for all k - 1 steps, so a step reads only the chain state
       // from shared memory (5 LDS.128 instead of 40 LDS.32 + 40 LDS.128 per thread: the loop was bound by the
       // shared-memory pipe) and the two halves of a dot product are joined with one shuffle.
-      const int pr = tid >> 1, half = tid & 1;
-      const bool mine = pr < B * CQ;
-      const int b = mine ? pr / CQ : 0, q = mine ? pr - b * CQ : 0;
+      // The chains of different minibatch rows are independent: every CTA of the cluster runs the k - 1 local steps for
+      // ITS rows only (ceil(B / 8) of them: an eighth of the draws and of the dot products) and the final states are
+      // exchanged once through distributed shared memory.
+      const int RPR = (B + CL - 1) / CL, b_lo = (int)rank * RPR, nb = max(0, min(RPR, B - b_lo)), nbq = nb * CQ;
+      // one warp per row (2 CQ <= 32 lanes: column quad x half): a row of the chain state is private to its warp, so the
+      // steps need no block barrier
+      const int half = lane & 1;
+      const bool mine = warp < nb && (lane >> 1) < CQ;
+      const int lb = mine ? warp : 0, q = mine ? (lane >> 1) : 0, b = mine ? b_lo + lb : 0, pr = lb * CQ + q;
       const int HH = ((H + 7) >> 3) << 2;                        // rows per half (multiple of 4, <= MH)
       float4 mreg[MH];
 #pragma unroll
@@ -359,28 +365,22 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * q);
         a0 = make_float4(c4.x + hb4.x, c4.y + hb4.y, c4.z + hb4.z, c4.w + hb4.w);
       }
-      // the uniforms of all k - 1 steps first, every Philox block once, spread over the whole CTA (inside the loop every
-      // warp would recompute them step after step: the loop was issue-bound on them)
-      {
-        const int nbq = B * CQ, lanes = NT / nbq;                 // threads per (row, quad): they take the steps round-robin
-        const int e = tid % nbq, s0 = tid / nbq, ub = e / CQ, uq = e - ub * CQ;
-        if (s0 < lanes) {
-#pragma unroll 2
-          for (int s = s0; s < p.k - 1; s += lanes) {
-            const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
-            const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
-            float u[4];
-            if (rs_h.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
-              const long long e0 = (long long)ub * H + 4 * uq;
-              const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs_h.c1, rs_h.c2, rs_h.c3, rs_h.k0, rs_h.k1);
-              u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
-            } else {
+      // the uniforms of all k - 1 steps first, every Philox block once, spread over the CTA (inside the loop every warp
+      // would recompute its block step after step: the loop was issue-bound on them)
+      for (int it = tid; it < (p.k - 1) * nbq; it += NT) {
+        const int s = it / nbq, e = it - s * nbq, ub = b_lo + e / CQ, uq = e % CQ;
+        const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
+        const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
+        float u[4];
+        if (rs_h.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
+          const long long e0 = (long long)ub * H + 4 * uq;
+          const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs_h.c1, rs_h.c2, rs_h.c3, rs_h.k0, rs_h.k1);
+          u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
+        } else {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) u[t] = 4 * uq + t < H ? rng_uniform(rs_h, (long long)ub * H + 4 * uq + t) : 2.f;
-            }
-            *reinterpret_cast<float4*>(Us + ((size_t)s * nbq + e) * 4) = make_float4(u[0], u[1], u[2], u[3]);
-          }
+          for (int t = 0; t < 4; ++t) u[t] = 4 * uq + t < H ? rng_uniform(rs_h, (long long)ub * H + 4 * uq + t) : 2.f;
         }
+        *reinterpret_cast<float4*>(Us + (size_t)it * 4) = make_float4(u[0], u[1], u[2], u[3]);
       }
       // chunk offsets of this half's part of the chain state (a chunk beyond the half, or beyond the row, re-reads
       // chunk 0 against zero rows of M: no branches in the loop)
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       const float4* up = reinterpret_cast<const float4*>(Us) + (mine ? pr : 0);
       __syncthreads();
       mark();   // uniforms of the local steps ready
-      for (int s = 0; s < p.k - 1; ++s) {
+      for (int s = 0; s < (warp < nb ? p.k - 1 : 0); ++s) {
         float4 a = a0;
 #pragma unroll
         for (int i4 = 0; i4 < MH / 4; ++i4) {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
             a.x = fmaf(hv[t], m4.x, a.x); a.y = fmaf(hv[t], m4.y, a.y); a.z = fmaf(hv[t], m4.z, a.z); a.w = fmaf(hv[t], m4.w, a.w);
           }
         }
-        const float4 u4 = up[(size_t)s * B * CQ];
+        const float4 u4 = mine ? up[(size_t)s * nbq] : make_float4(2.f, 2.f, 2.f, 2.f);
         a.x += __shfl_xor_sync(0xffffffffu, a.x, 1); a.y += __shfl_xor_sync(0xffffffffu, a.y, 1);
         a.z += __shfl_xor_sync(0xffffffffu, a.z, 1); a.w += __shfl_xor_sync(0xffffffffu, a.w, 1);
         float4 smp;
@@ -411,11 +411,20 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         smp.y = (4 * q + 1 < H && u4.y < sigmoid_fast_(a.y)) ? 1.f : 0.f;
         smp.z = (4 * q + 2 < H && u4.z < sigmoid_fast_(a.z)) ? 1.f : 0.f;
         smp.w = (4 * q + 3 < H && u4.w < sigmoid_fast_(a.w)) ? 1.f : 0.f;
-        __syncthreads();
+        __syncwarp();
         if (mine && half == 0) *reinterpret_cast<float4*>(hs + b * ldw + 4 * q) = smp;
-        __syncthreads();
+        __syncwarp();
         if (s == 0) mark();   // first local step
       }
+      // every CTA fetches the rows the other CTAs ran (the next cluster barrier — in the last Gibbs step — comes after
+      // these reads, before anybody overwrites its chain state again)
+      cluster_sync();
+      for (int it = tid; it < B * CQ; it += NT) {
+        const int rb = it / CQ, rq = it - rb * CQ;
+        const uint32_t owner = (uint32_t)(rb / RPR);
+        if (owner != rank) *reinterpret_cast<float4*>(hs + rb * ldw + 4 * rq) = ld_remote4(hs + rb * ldw + 4 * rq, owner);
+      }
+      __syncthreads();
       s_begin = p.k - 1;
       mark();   // local Gibbs steps done
     }
@@ -627,7 +636,7 @@ static Geometry plan(const mdbn_cd_args& a) {
   while (g.G > 1 && (size_t)g.G * hid > 48 * 1024) --g.G;
   g.use_m = a.kind == MDBN_GRBM && a.k > 1 && a.ldw <= 64 && a.B * g.CQ <= NT;
   static const bool no_mreg = getenv("MDBN_TINY_NO_MREG") != nullptr;
-  if (g.use_m && a.ldw <= 2 * tn::MH && 2 * a.B * g.CQ <= NT && !no_mreg) g.use_m = 2;      // M in registers
+  if (g.use_m && a.ldw <= 2 * tn::MH && 2 * g.CQ <= 32 && (a.B + CL - 1) / CL <= NT / 32 && !no_mreg) g.use_m = 2;      // M in registers
   g.off_M = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
   g.off_Mp = take(g.use_m ? (size_t)(a.H + 1) * a.ldw * 4 : 0);
   g.off_park = take(g.G > 1 ? (size_t)g.G * hid : 0);
