@@ -253,18 +253,51 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         // CTA and without any exchange; only the last step (whose visible means enter the statistics) goes
         // through the V visibles.  M does not depend on the minibatch: its partial over the owned rows is
         // exchanged behind the same cluster barrier as the positive phase.
-        for (int it = tid; it < (H + 1) * CQ; it += NT) {
-          const int i = it / CQ, q = it - i * CQ;
+        // 4 x 4 blocks of M, the owned rows dealt over four adjacent lanes (two quad loads per 16 FMAs; the scalar x quad
+        // form was bound by the shared-memory pipe), joined by two butterfly steps
+        for (int it = tid; it < CQ * CQ * 4; it += NT) {
+          const int blk = it >> 2, rg = it & 3, iq = blk / CQ, q = blk - iq * CQ;
+          float acc[4][4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+#pragma unroll 4
+          for (int r0 = 0; r0 < rows; r0 += 4) {                 // (same trip count in the four lanes)
+            const int r = min(r0 + rg, rows - 1);
+            const float4 a4 = r0 + rg < rows ? *reinterpret_cast<const float4*>(Ws + r * lds + 4 * iq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b4 = *reinterpret_cast<const float4*>(Ws + r * lds + 4 * q);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+          }
+          const unsigned am = 0xFu << (lane & ~3);               // the four lanes of this block
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              acc[x][y] += __shfl_xor_sync(am, acc[x][y], 1);
+              acc[x][y] += __shfl_xor_sync(am, acc[x][y], 2);
+            }
+          if (rg == 0) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              if (4 * iq + x < H)
+                *reinterpret_cast<float4*>(Mp + (4 * iq + x) * ldw + 4 * q) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+          }
+        }
+        // row H: vb . W (on the last threads of the CTA, which have no or few blocks)
+        for (int q = NT - 1 - tid; q < CQ; q += NT) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* col = i < H ? Ws + i : vbs;          // column i of the slab, or the visible bias (row H)
-          const int cs = i < H ? lds : 1;
 #pragma unroll 8
           for (int r = 0; r < rows; ++r) {
-            const float wi = col[r * cs];
+            const float wi = vbs[r];
             const float4 w4 = *reinterpret_cast<const float4*>(Ws + r * lds + 4 * q);
             a.x = fmaf(wi, w4.x, a.x); a.y = fmaf(wi, w4.y, a.y); a.z = fmaf(wi, w4.z, a.z); a.w = fmaf(wi, w4.w, a.w);
           }
-          *reinterpret_cast<float4*>(Mp + i * ldw + 4 * q) = a;
+          *reinterpret_cast<float4*>(Mp + H * ldw + 4 * q) = a;
         }
       }
       mark();
