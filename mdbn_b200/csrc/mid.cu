@@ -636,7 +636,8 @@ static Geometry plan(const mdbn_ctx* c, const mdbn_cd_args& a) {
   if (a.B < 1 || a.B > MAXB || a.ldw % 4 != 0) return g;     // (a noisy GRBM still feeds the visible MEAN upwards, src/rbm.py:669)
   if (((uintptr_t)a.W | (uintptr_t)a.W_speed | (uintptr_t)a.W_snap) & 15) return g;
   static const int og = getenv("MDBN_MID_GRID") ? atoi(getenv("MDBN_MID_GRID")) : 0;
-  g.grid = og > 0 && og < c->num_sms ? og : c->num_sms;
+  g.grid = og >= MAXB && og < c->num_sms ? og : c->num_sms;      // (the monitor of PCD takes one CTA per minibatch row)
+  if (g.grid < MAXB) return g;
   g.BTS = (a.B + 3) & ~3;
   g.CQ = a.ldw / 4;
   g.ldh = a.ldw;
