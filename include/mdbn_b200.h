@@ -11,7 +11,10 @@
  *   - all tensor arguments are CALLER-OWNED DEVICE pointers, fp32, row-major;
  *     `ld*` are row strides in elements.  W is [V,H] (src/rbm.py:100-109).
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not waited on.
- *   - the context owns only scratch memory; one context per (device, stream) user.
+ *   - the context owns only scratch memory (arenas, accumulators, grid-barrier words).  Calls on ONE context from
+ *     different streams are serialised by the library (a call on another stream than the previous one waits for it with
+ *     an event); users that want concurrency between streams create one context per stream.  Not thread-safe: one host
+ *     thread at a time per context.
  *   - samples are fp32 0.0/1.0 (src/rbm.py:210-212).
  */
 #ifndef MDBN_B200_H

@@ -37,6 +37,19 @@ void* ws_get(mdbn_ctx* c, int slot, size_t bytes) {
 
 }  // namespace mdbn
 
+namespace mdbn {
+void ctx_enter(mdbn_ctx* c, cudaStream_t st) {
+  if (c->has_last_stream && c->last_stream != st) {
+    if (!c->ev_order && cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming) != cudaSuccess) c->ev_order = nullptr;
+    // (a previous stream the caller has destroyed since has nothing left to wait for: errors are dropped)
+    if (c->ev_order && cudaEventRecord(c->ev_order, c->last_stream) == cudaSuccess) cudaStreamWaitEvent(st, c->ev_order, 0);
+    cudaGetLastError();
+  }
+  c->last_stream = st;
+  c->has_last_stream = true;
+}
+}  // namespace mdbn
+
 using namespace mdbn;
 
 extern "C" {
@@ -71,6 +84,7 @@ int mdbn_destroy(mdbn_ctx* c) {
   for (auto& b : c->ws)
     if (b.p) cudaFree(b.p);
   if (c->barrier) cudaFree(c->barrier);
+  if (c->ev_order) cudaEventDestroy(c->ev_order);
   delete c;
   return 0;
 }
@@ -118,6 +132,7 @@ int mdbn_propup(mdbn_ctx* c, const float* W, int ldw, const float* hbias, const 
   MDBN_CHECK(!sample_out || (rng && rng->mode != MDBN_RNG_NONE), "propup: sample_out needs an rng");
   MDBN_CHECK(!(rng && rng->mode == MDBN_RNG_BUFFER && sample_out) || rng->buffer, "propup: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
+  ctx_enter(c, (cudaStream_t)stream);
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
   if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, v, ldv))
     return tensor_propup(c, W, ldw, hbias, v, ldv, B, V, H, pre_out, mean_out, sample_out,
@@ -142,6 +157,7 @@ int mdbn_propdown(mdbn_ctx* c, const float* W, int ldw, const float* vbias, cons
   MDBN_CHECK(!needs_rng || (rng && rng->mode != MDBN_RNG_NONE), "propdown: sample_out needs an rng");
   MDBN_CHECK(!(needs_rng && rng->mode == MDBN_RNG_BUFFER) || rng->buffer, "propdown: rng buffer is NULL");
   MDBN_CUDA(cudaSetDevice(c->device));
+  ctx_enter(c, (cudaStream_t)stream);
   mdbn_rng none = {MDBN_RNG_NONE, nullptr, 0, 0};
   if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, h, ldh))
     return tensor_propdown(c, W, ldw, vbias, h, ldh, B, V, H, kind, noisy, pre_out, mean_out, sample_out,
@@ -155,6 +171,7 @@ int mdbn_free_energy(mdbn_ctx* c, const float* W, int ldw, const float* hbias, c
   MDBN_TRY(check_common(c, W, ldw, B, V, H));
   MDBN_CHECK(hbias && vbias && v && F_out && ldv >= V, "free_energy: bad arguments");
   MDBN_CUDA(cudaSetDevice(c->device));
+  ctx_enter(c, (cudaStream_t)stream);
   if (tensor_phase_wanted(V, H) && tensor_phase_supported(W, ldw, v, ldv))
     return tensor_free_energy(c, W, ldw, hbias, vbias, v, ldv, B, V, H, kind, F_out, (cudaStream_t)stream);
   return generic_free_energy(c, W, ldw, hbias, vbias, v, ldv, B, V, H, kind, F_out, (cudaStream_t)stream);
@@ -179,6 +196,7 @@ int mdbn_cd_step(mdbn_ctx* c, const mdbn_cd_args* a, void* stream) {
   if (a->phase == MDBN_PHASE_APPLY) MDBN_CHECK(a->B_total > 0, "cd_step: APPLY needs B_total");
   MDBN_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
+  ctx_enter(c, st);
   if (a->comm) {
     MDBN_CHECK(a->phase == MDBN_PHASE_FULL, "cd_step: comm goes with full steps only");
     return comm_cd_step(c, *a, st);
@@ -239,6 +257,7 @@ int mdbn_cd_steps(mdbn_ctx* c, const mdbn_cd_args* a, int n_steps, void* stream)
     MDBN_CHECK(a->data && a->ld_data >= a->V, "cd_steps: bad data/ld_data");
     MDBN_CHECK(!a->persistent || a->bit_i_idx, "cd_steps: PCD needs bit_i_idx");
     MDBN_CUDA(cudaSetDevice(c->device));
+    ctx_enter(c, (cudaStream_t)stream);
     if (use_tiny) return tiny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
     if (use_mid) return mid_cd_steps(c, *a, n_steps, (cudaStream_t)stream);
     return skinny_cd_steps(c, *a, n_steps, (cudaStream_t)stream);

@@ -21,6 +21,12 @@ struct mdbn_ctx {
   // data-parallel step: event the statistics path records once the V*H block of the packed buffer is complete
   cudaEvent_t ev_stats_w = nullptr;
   bool ev_stats_w_done = false;
+  // The scratch arenas, the accumulators and the grid-barrier words are shared by every call on this context: a call on
+  // another stream than the previous one first waits for the previous call (ctx_enter), so that users on different
+  // streams are serialised instead of racing
+  cudaStream_t last_stream = nullptr;
+  bool has_last_stream = false;
+  cudaEvent_t ev_order = nullptr;
 };
 
 namespace mdbn {
@@ -65,6 +71,9 @@ enum WsSlot {
   WS_TENSOR,     // tcgen05 path scratch
   WS_MISC,
 };
+
+// orders this call behind the previous call on the context when the stream changed (see mdbn_ctx::last_stream)
+void ctx_enter(mdbn_ctx* c, cudaStream_t st);
 
 // grow-only scratch; returns nullptr (and sets error) on failure
 void* ws_get(mdbn_ctx* c, int slot, size_t bytes);

@@ -794,6 +794,41 @@ def test_run_steps_equals_single_steps(kind, pcd, V, H, B):
         assert int(r1.bit_i_idx.item()) == int(r2.bit_i_idx.item()) == (n + 1) % V
 
 
+def test_two_streams_share_one_context():
+    """Two train functions issued from two different streams without any synchronisation in between share the device's
+    context (scratch arenas, accumulators, grid-barrier words): the library orders a call behind the previous call of the
+    context when the stream changes (api.cu ctx_enter), so the interleaved run equals the sequential one bit for bit."""
+    import torch
+    m = M()
+    shapes = [(O.GRBM, 2000, 72, 10), (O.RBM, 784, 500, 20)]      # row-slab kernel, broadcast kernel
+    n = 6
+
+    def run(two_streams):
+        fns, rbms = [], []
+        for i, (kind, V, H, B) in enumerate(shapes):
+            cls = m.GRBM if kind == O.GRBM else m.RBM
+            data = synth(kind, B * n, V, seed=50 + i)
+            W0 = O.init_W(np.random.RandomState(7 + i), V, H).astype(np.float32)
+            r = cls(n_visible=V, n_hidden=H, W=W0, theano_rng=m.RandomStreams(9 + i))
+            cost, upd = r.get_cost_updates(lr=0.02, k=1, lambda_1=0.01, lambda_2=0.1, batch_size=B)
+            f = r.make_train_fn(data, cost, upd)
+            f.sync = False
+            fns.append((f, torch.arange(B * n, dtype=torch.int32, device="cuda").view(n, B)))
+            rbms.append(r)
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()] if two_streams else [torch.cuda.current_stream()] * 2
+        for s in range(n):
+            for i, (f, idx) in enumerate(fns):
+                with torch.cuda.stream(streams[i]):
+                    f(idx[s], 0.5)
+        torch.cuda.synchronize()
+        return [[getattr(r, name).get_value().copy() for name in ("W", "hbias", "vbias", "W_speed")] for r in rbms]
+    a, b = run(False), run(True)
+    for pa, pb in zip(a, b):
+        for x, y in zip(pa, pb):
+            assert np.array_equal(x, y)
+
+
 # ---------------------------------------------------------------------------
 # 8f: a checkpoint written by the reference's save_network loads into working DBNs
 # ---------------------------------------------------------------------------
