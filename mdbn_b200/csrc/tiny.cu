@@ -563,49 +563,67 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
     }
 
     // =============================== statistics + update (owned rows, in shared memory) ===============================
-    for (int it = tid; it < rows * CQ; it += NT) {
-      const int r = it / CQ, q = it - r * CQ;
-      float gs[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int b = 0; b < B; ++b) {
-        const float a = v0s[r * BTS + b], n = nvs[r * BTS + b];
-        const float4 ph4 = *reinterpret_cast<const float4*>(phs + b * ldw + 4 * q);
-        const float4 nh4 = *reinterpret_cast<const float4*>(nhs + b * ldw + 4 * q);
-        gs[0] = fmaf(a, ph4.x, gs[0]); gs[0] = fmaf(-n, nh4.x, gs[0]);
-        gs[1] = fmaf(a, ph4.y, gs[1]); gs[1] = fmaf(-n, nh4.y, gs[1]);
-        gs[2] = fmaf(a, ph4.z, gs[2]); gs[2] = fmaf(-n, nh4.z, gs[2]);
-        gs[3] = fmaf(a, ph4.w, gs[3]); gs[3] = fmaf(-n, nh4.w, gs[3]);
-      }
-      float4 w4 = *reinterpret_cast<float4*>(Ws + r * lds + 4 * q), s4 = *reinterpret_cast<float4*>(Ss + r * lds + 4 * q);
-      float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.wc != 0.f) n4 = __ldg(reinterpret_cast<const float4*>(p.Wsnap + (size_t)(row0 + r) * ldw + 4 * q));
-      float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, nv4[4] = {n4.x, n4.y, n4.z, n4.w};
-      float wo[4], so[4];
+    // thread = (pair of owned rows, column quad): the hidden means of a minibatch row are read once for the two rows and
+    // one round covers the slab (one row per thread left 512 threads 700 items: two rounds, the second a third full)
+    {
+      const int half = (rows + 1) >> 1;
+      auto finish = [&](int r, int q, const float (&gs)[4]) {
+        float4 w4 = *reinterpret_cast<float4*>(Ws + r * lds + 4 * q), s4 = *reinterpret_cast<float4*>(Ss + r * lds + 4 * q);
+        float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.wc != 0.f) n4 = __ldg(reinterpret_cast<const float4*>(p.Wsnap + (size_t)(row0 + r) * ldw + 4 * q));
+        float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, nv4[4] = {n4.x, n4.y, n4.z, n4.w};
+        float wo[4], so[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float gw = gs[c] * p.inv_bnom - p.wc * nv4[c];                  // src/rbm.py:411-415
-        float mult = p.decay;
-        if (p.c1 != 0.f) {
-          const float t = fabsf(wv[c]) + 0.001f;                        // :347-350, one reciprocal
-          const float invD = t * rcp_approx(t + p.c1);
-          gw *= invD;
-          mult *= invD;                                                 // :353-356
+        for (int c = 0; c < 4; ++c) {
+          float gw = gs[c] * p.inv_bnom - p.wc * nv4[c];                  // src/rbm.py:411-415
+          float mult = p.decay;
+          if (p.c1 != 0.f) {
+            const float t = fabsf(wv[c]) + 0.001f;                        // :347-350, one reciprocal
+            const float invD = t * rcp_approx(t + p.c1);
+            gw *= invD;
+            mult *= invD;                                                 // :353-356
+          }
+          so[c] = gw + (sv[c] - gw) * p.mom;                              // :361
+          wo[c] = 4 * q + c < H ? wv[c] * mult + sv[c] * p.lr : wv[c];    // :364 (OLD speed); padding columns stay zero
+          if (4 * q + c >= H) so[c] = sv[c];
         }
-        so[c] = gw + (sv[c] - gw) * p.mom;                              // :361
-        wo[c] = 4 * q + c < H ? wv[c] * mult + sv[c] * p.lr : wv[c];    // :364 (OLD speed); padding columns stay zero
-        if (4 * q + c >= H) so[c] = sv[c];
+        *reinterpret_cast<float4*>(Ws + r * lds + 4 * q) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+        *reinterpret_cast<float4*>(Ss + r * lds + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
+      };
+      for (int it = tid; it < half * CQ; it += NT) {
+        const int r0 = it / CQ, q = it - r0 * CQ, r1 = r0 + half;
+        const bool two = r1 < rows;
+        const float* a0p = v0s + r0 * BTS; const float* n0p = nvs + r0 * BTS;
+        const float* a1p = v0s + (two ? r1 : r0) * BTS; const float* n1p = nvs + (two ? r1 : r0) * BTS;
+        float g0[4] = {0.f, 0.f, 0.f, 0.f}, g1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int b = 0; b < B; ++b) {
+          const float4 ph4 = *reinterpret_cast<const float4*>(phs + b * ldw + 4 * q);
+          const float4 nh4 = *reinterpret_cast<const float4*>(nhs + b * ldw + 4 * q);
+          const float a0 = a0p[b], n0 = -n0p[b], a1 = a1p[b], n1 = -n1p[b];
+          g0[0] = fmaf(a0, ph4.x, g0[0]); g0[0] = fmaf(n0, nh4.x, g0[0]);
+          g0[1] = fmaf(a0, ph4.y, g0[1]); g0[1] = fmaf(n0, nh4.y, g0[1]);
+          g0[2] = fmaf(a0, ph4.z, g0[2]); g0[2] = fmaf(n0, nh4.z, g0[2]);
+          g0[3] = fmaf(a0, ph4.w, g0[3]); g0[3] = fmaf(n0, nh4.w, g0[3]);
+          g1[0] = fmaf(a1, ph4.x, g1[0]); g1[0] = fmaf(n1, nh4.x, g1[0]);
+          g1[1] = fmaf(a1, ph4.y, g1[1]); g1[1] = fmaf(n1, nh4.y, g1[1]);
+          g1[2] = fmaf(a1, ph4.z, g1[2]); g1[2] = fmaf(n1, nh4.z, g1[2]);
+          g1[3] = fmaf(a1, ph4.w, g1[3]); g1[3] = fmaf(n1, nh4.w, g1[3]);
+        }
+        finish(r0, q, g0);
+        if (two) finish(r1, q, g1);
       }
-      *reinterpret_cast<float4*>(Ws + r * lds + 4 * q) = make_float4(wo[0], wo[1], wo[2], wo[3]);
-      *reinterpret_cast<float4*>(Ss + r * lds + 4 * q) = make_float4(so[0], so[1], so[2], so[3]);
     }
-    for (int r = tid; r < rows; r += NT) {                       // visible bias  src/rbm.py:417
+    // biases on the LAST warps of the CTA (they have no or few row pairs): visible bias of the owned rows
+    // (src/rbm.py:417), hidden bias (:416 — every CTA, identical result); nothing above writes what they read
+    for (int r = NT - 1 - tid; r < rows; r += NT) {
       float gsum = 0.f;
       for (int b = 0; b < B; ++b) gsum += v0s[r * BTS + b] - nvs[r * BTS + b];
       const float gb = gsum * p.inv_b, sv = svbs[r];
       svbs[r] = gb + (sv - gb) * p.mom;
       vbs[r] = vbs[r] + sv * p.lr;
     }
-    __syncthreads();                                             // (phs / nhs are still read above)
-    for (int j = tid; j < H; j += NT) {                          // hidden bias  :416 — every CTA, identical result
+    for (int j = (NT - 1 - tid + NT - rows % NT) % NT; j < H; j += NT) {      // (threads in front of the visible-bias ones)
       float gsum = 0.f;
       for (int b = 0; b < B; ++b) gsum += phs[b * ldw + j] - nhs[b * ldw + j];
       const float gb = gsum * p.inv_b, sv = shbs[j];
