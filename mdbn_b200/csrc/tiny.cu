@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
   };
 
   int* sidx = reinterpret_cast<int*>(misc) + 48;
+  // minibatch rows whose local Gibbs steps this CTA runs (use_m == 2)
+  const int RPR = (B + CL - 1) / CL, b_lo = (int)rank * RPR, nb = max(0, min(RPR, B - b_lo)), nbq = nb * CQ;
 
   for (int step = 0; step < p.n_steps; ++step) {
     const int* idxp = p.idx ? p.idx + (size_t)step * B : nullptr;
@@ -304,16 +306,37 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       cluster_sync();
       mark();
       if (p.use_m) {
+        // (use_m == 2) the uniforms of this CTA's rows for the k - 1 local Gibbs steps are drawn HERE, between the remote
+        // loads and their sum: a Philox block per thread rides on the DSMEM latency
+        const int n_u = p.use_m == 2 ? (p.k - 1) * nbq : 0;
+        auto draw = [&](int ui) {
+          const int s = ui / nbq, e = ui - s * nbq, ub = b_lo + e / CQ, uq = e % CQ;
+          const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
+          const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
+          float u[4];
+          if (rs_h.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
+            const long long e0 = (long long)ub * H + 4 * uq;
+            const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs_h.c1, rs_h.c2, rs_h.c3, rs_h.k0, rs_h.k1);
+            u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) u[t] = 4 * uq + t < H ? rng_uniform(rs_h, (long long)ub * H + 4 * uq + t) : 2.f;
+          }
+          *reinterpret_cast<float4*>(Us + (size_t)ui * 4) = make_float4(u[0], u[1], u[2], u[3]);
+        };
+        int ui = tid;
         for (int it = tid; it < (H + 1) * CQ; it += NT) {
           const float* lp = Mp + 4 * it + (it / CQ) * (ldw - 4 * CQ);
-          float4 sm = ld_remote4(lp, 0);
+          float4 v[CL];
 #pragma unroll
-          for (uint32_t c = 1; c < CL; ++c) {
-            const float4 o = ld_remote4(lp, c);
-            sm.x += o.x; sm.y += o.y; sm.z += o.z; sm.w += o.w;
-          }
+          for (uint32_t c = 0; c < CL; ++c) v[c] = ld_remote4(lp, c);
+          if (ui < n_u) { draw(ui); ui += NT; }
+          float4 sm = v[0];
+#pragma unroll
+          for (uint32_t c = 1; c < CL; ++c) { sm.x += v[c].x; sm.y += v[c].y; sm.z += v[c].z; sm.w += v[c].w; }
           *reinterpret_cast<float4*>(Ms + (lp - Mp)) = sm;
         }
+        for (; ui < n_u; ui += NT) draw(ui);
       }
       const RngSeg rs0 = seg(0, 0, step);
       all_reduce(my, [&](int b, int j0, const float (&pre)[4]) {
@@ -379,7 +402,6 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       // The chains of different minibatch rows are independent: every CTA of the cluster runs the k - 1 local steps for
       // ITS rows only (ceil(B / 8) of them: an eighth of the draws and of the dot products) and the final states are
       // exchanged once through distributed shared memory.
-      const int RPR = (B + CL - 1) / CL, b_lo = (int)rank * RPR, nb = max(0, min(RPR, B - b_lo)), nbq = nb * CQ;
       // one warp per row (2 CQ <= 32 lanes: column quad x half): a row of the chain state is private to its warp, so the
       // steps need no block barrier
       const int half = lane & 1;
@@ -398,23 +420,6 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
         const float4 hb4 = *reinterpret_cast<const float4*>(hbs + 4 * q);
         a0 = make_float4(c4.x + hb4.x, c4.y + hb4.y, c4.z + hb4.z, c4.w + hb4.w);
       }
-      // the uniforms of all k - 1 steps first, every Philox block once, spread over the CTA (inside the loop every warp
-      // would recompute its block step after step: the loop was issue-bound on them)
-      for (int it = tid; it < (p.k - 1) * nbq; it += NT) {
-        const int s = it / nbq, e = it - s * nbq, ub = b_lo + e / CQ, uq = e % CQ;
-        const long long ubase = (long long)B * H + (long long)s * p.u_step_stride;
-        const RngSeg rs_h = seg(ubase + p.u_off_h, 2u + 2u * s, step);
-        float u[4];
-        if (rs_h.mode != MDBN_RNG_BUFFER && (H & 3) == 0) {
-          const long long e0 = (long long)ub * H + 4 * uq;
-          const Philox4 x = philox4x32_10((uint32_t)(e0 >> 2), rs_h.c1, rs_h.c2, rs_h.c3, rs_h.k0, rs_h.k1);
-          u[0] = u24(x.x); u[1] = u24(x.y); u[2] = u24(x.z); u[3] = u24(x.w);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) u[t] = 4 * uq + t < H ? rng_uniform(rs_h, (long long)ub * H + 4 * uq + t) : 2.f;
-        }
-        *reinterpret_cast<float4*>(Us + (size_t)it * 4) = make_float4(u[0], u[1], u[2], u[3]);
-      }
       // chunk offsets of this half's part of the chain state (a chunk beyond the half, or beyond the row, re-reads
       // chunk 0 against zero rows of M: no branches in the loop)
       int hoff[MH / 4];
@@ -422,8 +427,7 @@ __global__ void __launch_bounds__(NT, 1) cd_tiny_kernel(const Params p) {
       for (int i4 = 0; i4 < MH / 4; ++i4) hoff[i4] = (4 * i4 < HH && HH * half + 4 * i4 < ldw) ? 4 * i4 : 0;
       const float* hrow = hs + b * ldw + HH * half;
       const float4* up = reinterpret_cast<const float4*>(Us) + (mine ? pr : 0);
-      __syncthreads();
-      mark();   // uniforms of the local steps ready
+      mark();   // registers of the local steps ready (the uniforms were drawn under the all-reduce of M)
       for (int s = 0; s < (warp < nb ? p.k - 1 : 0); ++s) {
         float4 a = a0;
 #pragma unroll

@@ -1,5 +1,5 @@
 set -x
-O=gpurun_out/tiny6
+O=gpurun_out/tiny7
 mkdir -p $O
 python -m pytest tests/test_gpu_parity.py -x -q -k "tiny or aml or small" 2>&1 | tail -5 > $O/tests.log
 cat $O/tests.log
