@@ -191,3 +191,43 @@ def test_rbm_grad_is_free_energy_gradient():
             L.W[i, j] = w
             num[i, j] = (a - b) / 2e-6
     np.testing.assert_allclose(g, num, atol=1e-8)
+
+
+def test_symbolic_gradient_identity_grbm():
+    """the reference's alternative `compute_symbolic_grad` (src/rbm.py:378-390) differentiates
+    mean F(v0) - mean F(chain_end) with the chain end held constant.  For the error-free GRBM (mean-field visibles:
+    chain end == negative visible mean) that gradient IS the statistics `compute_rbm_grad` builds (:392-419).  Checked on
+    the oracle in fp64 with central differences of its own free_energy against the packed statistics of cd_stats."""
+    rs = np.random.RandomState(11)
+    V, H, B, k = 7, 5, 4, 2
+    L = O.Layer(V, H, O.GRBM, W=rs.randn(V, H) * 0.3, hbias=rs.randn(H) * 0.1, vbias=rs.randn(V) * 0.1)
+    v0 = rs.randn(B, V)
+    U = rs.uniform(size=O.u_size(O.GRBM, True, B, V, H, k))
+    packed = O.cd_stats(L, v0, U, k=k)
+    gW, ghb, gvb = packed[:V * H].reshape(V, H) / B, packed[V * H:V * H + H] / B, packed[V * H + H:V * H + H + V] / B
+    # chain end, replayed exactly as cd_stats runs it
+    u = O._views(U, O.GRBM, True, B, V, H, k)
+    _, _, h = O.sample_h_given_v(L, v0, u["hpos"])
+    for s in range(k):
+        _, vk, _, _, _, h = O.gibbs_hvh(L, h, u.get("v%d" % s), u["h%d" % s])
+
+    def cost():
+        return O.free_energy(L, v0).mean() - O.free_energy(L, vk).mean()
+
+    def numgrad(arr):
+        g = np.zeros_like(arr)
+        it = np.nditer(arr, flags=["multi_index"])
+        for _ in it:
+            i = it.multi_index
+            old = arr[i]
+            arr[i] = old + 1e-6
+            cp = cost()
+            arr[i] = old - 1e-6
+            cm = cost()
+            arr[i] = old
+            g[i] = (cp - cm) / 2e-6
+        return g
+    # the update direction is MINUS the gradient of the cost (src/rbm.py:386-390)
+    np.testing.assert_allclose(-numgrad(L.W), gW, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(-numgrad(L.hbias), ghb, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(-numgrad(L.vbias), gvb, rtol=1e-6, atol=1e-8)
