@@ -11,7 +11,7 @@ import torch
 from .mlp import HiddenLayer
 from .rbm import RBM, GRBM
 from .rng import RandomStreams
-from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx
+from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx, IndexFeeder
 
 
 class _LowerStack:
@@ -126,6 +126,7 @@ class DBN(object):
         idx_minibatches, minibatches = get_minibatches_idx(n_data, batch_size, shuffle=True)      # :420
         n_train_batches = idx_minibatches[-1] + 1
         self.history = []
+        feeder = IndexFeeder(self.device, n_data)
         for i in range(self.n_layers):
             momentum = 0.0 if isinstance(self.rbm_layers[i], GRBM) else 0.6                       # :430-433
             best_cost = numpy.inf
@@ -140,7 +141,7 @@ class DBN(object):
             while (epoch < pretraining_epochs[i]) and (not done_looping):
                 epoch = epoch + 1
                 idx_minibatches, minibatches = get_minibatches_idx(n_data, batch_size, shuffle=True)
-                flat = torch.as_tensor(numpy.concatenate(minibatches)).to(self.device)   # one H2D per epoch
+                flat = feeder.upload(minibatches)      # one asynchronous H2D per epoch (pinned ring: no stream sync)
                 if not isinstance(self.rbm_layers[i], GRBM) and epoch == 6:
                     momentum = 0.9                                                                # :452-453
                 lo, mb = 0, 0

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from .rng import RandomStreams, BufferStreams, ExplicitBuffer
-from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx
+from .utils import Shared, as_device_matrix, default_device, get_minibatches_idx, IndexFeeder
 
 _PAD = 8   # W rows padded to 8 floats: 16-byte aligned bulk copies + whole 8-column MMA tiles
 
@@ -563,12 +563,13 @@ class RBM(object):
         start_time = timeit.default_timer()
         momentum = initial_momentum
         history = []
+        feeder = IndexFeeder(self.device, n_train_data)
         for epoch in range(training_epochs):
             if epoch == 6:                                                    # :584 (0-based)
                 momentum = final_momentum
             _, minibatches = get_minibatches_idx(n_train_data, batch_size, shuffle=True)
             # one H2D copy of the whole epoch's index list instead of one per step
-            flat = torch.as_tensor(numpy.concatenate(minibatches)).to(self.device)
+            flat = feeder.upload(minibatches)
             costs = torch.empty(len(minibatches), dtype=torch.float32, device=self.device)
             lo, i = 0, 0
             while i < len(minibatches):          # runs of equal-length minibatches: one chained launch each

@@ -104,3 +104,32 @@ def get_minibatches_idx(n, batch_size, shuffle=False):
     if start != n:
         minibatches.append(idx_list[start:])
     return range(len(minibatches)), minibatches
+
+
+class IndexFeeder:
+    """Epoch index lists host -> device without stalling the epoch loop.  `torch.as_tensor(a).to(device)` from pageable
+    memory ends in a stream synchronise: the host waits for the previous epoch's launch before it can enqueue the next one,
+    and the GPU idles while the host shuffles (measured on 559->40, k = 10: 27.9 us per step wall against 22.9 us of
+    kernel).  Here the list goes through a ring of pinned buffers with asynchronous copies; a slot is reused `depth`
+    epochs later, after the event recorded behind its copy."""
+
+    def __init__(self, device, capacity, depth=4):
+        self.device = device
+        self.ring = [torch.empty(int(capacity), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.events = [None] * depth
+        self.n = 0
+
+    def upload(self, arrays):
+        """arrays: list of int32 numpy index arrays (the minibatches of an epoch) -> one flat int32 device tensor"""
+        slot = self.n % len(self.ring)
+        self.n += 1
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()
+        total = sum(len(a) for a in arrays)
+        host = self.ring[slot][:total]
+        numpy.concatenate(arrays, out=host.numpy())
+        dev = host.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[slot] = ev
+        return dev
