@@ -10,11 +10,15 @@
 //              sigmoid and the Bernoulli draw are computed once, by the owner, and published as [B, H] in global memory;
 //   propdown : a CTA owns a slice of visible ROWS and sums over all hidden units (whole [B, H] sample in shared memory,
 //              its rows of W contiguous): complete again; the result is published as [V, B];
-//   between two propagations: ONE grid barrier, then every CTA copies the 40-80 KB panel it needs from L2;
+//   between two propagations: ONE grid barrier, then every CTA copies the 40-135 KB panel it needs from L2 (cp.async);
+//   minibatch: every CTA gathers only its OWN rows and publishes them as rows of the visible panel (in a chained launch
+//              ahead of the barrier that ends the previous step); the whole minibatch then arrives as a panel copy;
 //   update   : the row owner updates its rows of W / W_speed (it kept its rows of v0 and of the negative means), reading
-//              the positive / negative hidden means of all columns from the published panels; biases by their owners.
-// No atomics, no redundant rebuild; 2k + 2 barriers per step.  Same arithmetic contract as the other paths (fp32,
-// src/rbm.py semantics, Philox draws indexed by element or the caller's uniform buffer).
+//              the positive / negative hidden means of all columns from the published panels; biases by their owners;
+//   PCD      : pseudo-likelihood partials per CTA, one minibatch row summed on each of the last CTAs of the grid.
+// No atomics, no redundant rebuild; 2k + 2 barriers per step (+ 1 at the start of a launch), fixed summation orders.  Same
+// arithmetic contract as the other paths (fp32, src/rbm.py semantics, Philox draws indexed by element or the caller's
+// uniform buffer).  Measured: DESIGN.md 4.4, profiles/r2_mid_kernel_*.txt.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
